@@ -1,0 +1,360 @@
+// extern "C" entry points declared in include/lss_b200.h.
+#include "lss_common.cuh"
+#include "lss_geometry.cuh"
+#include "lss_pool.cuh"
+#include "lss_sort.cuh"
+
+namespace lss {
+char* cuda_error_buffer() {
+  static thread_local char buf[256] = {0};
+  return buf;
+}
+
+static int check_shape(const LssShape* s) {
+  if (!s) return LSS_ERR_NULL_POINTER;
+  if (s->B <= 0 || s->N <= 0 || s->D <= 0 || s->fH <= 0 || s->fW <= 0 || s->C <= 0)
+    return LSS_ERR_BAD_DIMENSION;
+  const long long P = (long long)s->B * s->N * s->D * s->fH * s->fW;
+  if (P >= (1ll << 30)) return LSS_ERR_BAD_DIMENSION;
+  return LSS_OK;
+}
+static inline long long shape_points(const LssShape* s) {
+  return (long long)s->B * s->N * s->D * s->fH * s->fW;
+}
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static int launch_geometry(const GeomArgs& ga, const GridDev& g, const LssShape* sh,
+                           const PointOut& out, const SortDigits* sd, cudaStream_t st) {
+  const int ppc = sh->D * sh->fH * sh->fW;
+  int chunks = (ppc + 2047) / 2048;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, sh->B * sh->N);
+  FastDiv div_hw(sh->fH * sh->fW), div_w(sh->fW);
+  if (sd && sd->hist) {
+    const size_t smem = (size_t)sd->passes * sd->stride * sizeof(uint32_t);
+    geometry_rank_kernel<true><<<grid, kGeomThreads, smem, st>>>(ga, g, div_hw, div_w, out, *sd);
+  } else {
+    SortDigits none;
+    memset(&none, 0, sizeof(none));
+    geometry_rank_kernel<false><<<grid, kGeomThreads, 0, st>>>(ga, g, div_hw, div_w, out, none);
+  }
+  LSS_LAUNCH_CHECK("geometry_rank_kernel");
+  return LSS_OK;
+}
+
+static int launch_intervals(const int32_t* sorted_ranks, long long P, const GridDev& g,
+                            uint8_t* last_mask, int32_t* cell_range, int32_t* counts,
+                            uint32_t* wipe, long long wipe_words, cudaStream_t st) {
+  IntervalArgs a;
+  a.sorted_ranks = sorted_ranks; a.P = P; a.g = g;
+  a.div_b = FastDiv(g.B); a.div_z = FastDiv(g.nx[2]); a.div_y = FastDiv(g.nx[1]);
+  a.last_mask = last_mask; a.cell_range = reinterpret_cast<int2*>(cell_range); a.counts = counts;
+  a.wipe = wipe; a.wipe_words = wipe_words;
+  long long blocks = (P + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  intervals_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  LSS_LAUNCH_CHECK("intervals_kernel");
+  return LSS_OK;
+}
+template <int kLanes, int kChunks>
+static int launch_bwd(const PoolBwdArgs& a, int blocks, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    LSS_CUDA_TRY(cudaFuncSetAttribute(liftsplat_bwd_nhwc_kernel<kLanes, kChunks>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "cudaFuncSetAttribute(bwd smem)");
+  }
+  liftsplat_bwd_nhwc_kernel<kLanes, kChunks><<<blocks, 256, smem, st>>>(a);
+  LSS_LAUNCH_CHECK("liftsplat_bwd_nhwc_kernel");
+  return LSS_OK;
+}
+
+}  // namespace lss
+
+using namespace lss;
+
+extern "C" {
+
+int lss_abi_version(void) { return LSS_ABI_VERSION; }
+
+const char* lss_status_string(int status) {
+  switch (status) {
+    case LSS_OK: return "ok";
+    case LSS_ERR_NULL_POINTER: return "null pointer argument";
+    case LSS_ERR_BAD_DIMENSION: return "bad dimension (non-positive, too large, or inconsistent)";
+    case LSS_ERR_MISALIGNED: return "pointer not 16-byte aligned or C not a multiple of 4";
+    case LSS_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case LSS_ERR_UNSUPPORTED: return "unsupported configuration";
+    case LSS_ERR_CUDA: return "CUDA error (see lss_last_cuda_error)";
+    default: return "unknown status";
+  }
+}
+
+const char* lss_last_cuda_error(void) { return cuda_error_buffer(); }
+
+int lss_camera_prep(const float* d_rots, const float* d_intrins, const float* d_post_rots,
+                    int32_t n_cams, float* d_inv_post_rots, float* d_combine, void* stream) {
+  LSS_REQUIRE(d_rots && d_intrins && d_post_rots && d_inv_post_rots && d_combine, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(n_cams > 0, LSS_ERR_BAD_DIMENSION);
+  camera_prep_kernel<<<(n_cams + 63) / 64, 64, 0, as_stream(stream)>>>(
+      d_rots, d_intrins, d_post_rots, n_cams, d_inv_post_rots, d_combine);
+  LSS_LAUNCH_CHECK("camera_prep_kernel");
+  return LSS_OK;
+}
+
+int lss_quantize_rank(const float* d_geom, const LssGrid* grid, int32_t B, int64_t P,
+                      int32_t* d_coords, uint8_t* d_kept, int32_t* d_ranks, int32_t* d_cells,
+                      void* stream) {
+  LSS_REQUIRE(d_geom && d_ranks, LSS_ERR_NULL_POINTER);
+  GridDev g;
+  int rc = make_grid(grid, B, &g);
+  if (rc) return rc;
+  LSS_REQUIRE(P > 0 && P < (1ll << 30) && P % B == 0, LSS_ERR_BAD_DIMENSION);
+  PointOut out{d_coords, d_kept, d_ranks, d_cells};
+  SortDigits none;
+  memset(&none, 0, sizeof(none));
+  long long blocks = (P + kGeomThreads - 1) / kGeomThreads;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  quantize_rank_kernel<false><<<(unsigned)blocks, kGeomThreads, 0, as_stream(stream)>>>(
+      d_geom, g, P, P / B, out, none);
+  LSS_LAUNCH_CHECK("quantize_rank_kernel");
+  return LSS_OK;
+}
+
+int lss_geometry_rank(const float* d_us, const float* d_vs, const float* d_ds,
+                      const float* d_inv_post_rots, const float* d_post_trans,
+                      const float* d_combine, const float* d_trans, const LssGrid* grid,
+                      const LssShape* shape, float* d_geom, int32_t* d_coords, uint8_t* d_kept,
+                      int32_t* d_ranks, int32_t* d_cells, void* stream) {
+  LSS_REQUIRE(d_us && d_vs && d_ds && d_inv_post_rots && d_post_trans && d_combine && d_trans &&
+                  d_ranks, LSS_ERR_NULL_POINTER);
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  GridDev g;
+  rc = make_grid(grid, shape->B, &g);
+  if (rc) return rc;
+  GeomArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.us = d_us; ga.vs = d_vs; ga.ds = d_ds;
+  ga.inv_post_rots = d_inv_post_rots; ga.post_trans = d_post_trans;
+  ga.combine = d_combine; ga.trans = d_trans;
+  ga.raw = 0; ga.N = shape->N; ga.D = shape->D; ga.fH = shape->fH; ga.fW = shape->fW;
+  ga.geom = d_geom;
+  PointOut out{d_coords, d_kept, d_ranks, d_cells};
+  return launch_geometry(ga, g, shape, out, nullptr, as_stream(stream));
+}
+
+size_t lss_sort_workspace_bytes(int64_t P, int32_t n_cells) {
+  if (P <= 0 || n_cells <= 0) return 0;
+  return make_sort_plan(P, n_cells).total_bytes;
+}
+
+int lss_sort_ranks(const int32_t* d_ranks, int64_t P, int32_t n_cells, int32_t* d_sorted_ranks,
+                   int32_t* d_sorted_points, void* d_workspace, size_t workspace_bytes,
+                   void* stream) {
+  LSS_REQUIRE(d_ranks && d_sorted_ranks && d_sorted_points && d_workspace, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(P > 0 && P < (1ll << 30) && n_cells > 0 && n_cells < 0x7fffffff, LSS_ERR_BAD_DIMENSION);
+  LSS_REQUIRE(aligned16(d_workspace), LSS_ERR_MISALIGNED);
+  const SortPlan s = make_sort_plan(P, n_cells);
+  LSS_REQUIRE(workspace_bytes >= s.total_bytes, LSS_ERR_WORKSPACE_TOO_SMALL);
+  cudaStream_t st = as_stream(stream);
+  char* w = static_cast<char*>(d_workspace);
+  LSS_CUDA_TRY(cudaMemsetAsync(w + s.off_control, 0, s.control_bytes, st), "memset sort control");
+  SortDigits sd = sort_digits(s, d_workspace);
+  long long blocks = (P + 256 * 8 - 1) / (256 * 8);
+  const long long cap = (long long)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  histogram_kernel<<<(unsigned)blocks, 256, (size_t)sd.passes * sd.stride * 4, st>>>(d_ranks, P, sd);
+  LSS_LAUNCH_CHECK("histogram_kernel");
+  return run_sort_passes(s, d_ranks, d_sorted_ranks, d_sorted_points, P, d_workspace, st);
+}
+
+int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid, int32_t B,
+                  uint8_t* d_last_mask, int32_t* d_cell_range, int32_t* d_counts, void* stream) {
+  LSS_REQUIRE(d_sorted_ranks && d_cell_range, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(P > 0 && P < (1ll << 30), LSS_ERR_BAD_DIMENSION);
+  GridDev g;
+  int rc = make_grid(grid, B, &g);
+  if (rc) return rc;
+  return launch_intervals(d_sorted_ranks, P, g, d_last_mask, d_cell_range, d_counts, nullptr, 0,
+                          as_stream(stream));
+}
+
+static int pool_fwd_common(bool fused, const float* d_depth_t, const float* d_feat_t,
+                           const float* d_x, const int32_t* d_sorted_points,
+                           const int32_t* d_cell_range, const LssGrid* grid, int32_t B, int32_t C,
+                           int32_t D, int32_t HW, long long dhw, int32_t layout, float* d_bev,
+                           cudaStream_t st) {
+  LSS_REQUIRE(d_sorted_points && d_cell_range && d_bev, LSS_ERR_NULL_POINTER);
+  GridDev g;
+  int rc = make_grid(grid, B, &g);
+  if (rc) return rc;
+  LSS_REQUIRE(C > 0 && C % 4 == 0, LSS_ERR_MISALIGNED);
+  LSS_REQUIRE(aligned16(d_bev), LSS_ERR_MISALIGNED);
+  LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
+  PoolFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.depth_t = d_depth_t; a.feat_t = reinterpret_cast<const float4*>(d_feat_t);
+  a.x = reinterpret_cast<const float4*>(d_x);
+  a.sorted_points = d_sorted_points; a.cell_range = reinterpret_cast<const int2*>(d_cell_range);
+  a.bev = reinterpret_cast<float4*>(d_bev);
+  a.G = C / 4; a.D = D; a.HW = HW;
+  a.n_elems = (long long)g.n_cells * a.G;
+  LSS_REQUIRE(a.n_elems < (1ll << 31), LSS_ERR_BAD_DIMENSION);
+  a.div_g = FastDiv(a.G);
+  a.div_dhw = FastDiv((uint32_t)(dhw > 0 ? dhw : 1)); a.div_hw = FastDiv((uint32_t)(HW > 0 ? HW : 1));
+  long long blocks = (a.n_elems + 255) / 256;
+  const long long cap = (long long)sm_count() * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  if (fused) pool_fwd_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a);
+  else pool_fwd_nhwc_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a);
+  LSS_LAUNCH_CHECK("pool_fwd_nhwc_kernel");
+  return LSS_OK;
+}
+
+int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points,
+                       const int32_t* d_cell_range, const LssGrid* grid, int32_t B, int32_t C,
+                       int32_t layout, float* d_bev, void* stream) {
+  LSS_REQUIRE(d_x, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(aligned16(d_x), LSS_ERR_MISALIGNED);
+  return pool_fwd_common(false, nullptr, nullptr, d_x, d_sorted_points, d_cell_range, grid, B, C, 1, 1,
+                         1, layout, d_bev, as_stream(stream));
+}
+
+int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGrid* grid,
+                       int32_t B, int32_t C, int64_t P, int32_t layout, float* d_dx,
+                       void* stream) {
+  LSS_REQUIRE(d_dbev && d_cells && d_dx, LSS_ERR_NULL_POINTER);
+  GridDev g;
+  int rc = make_grid(grid, B, &g);
+  if (rc) return rc;
+  LSS_REQUIRE(C > 0 && C % 4 == 0 && aligned16(d_dbev) && aligned16(d_dx), LSS_ERR_MISALIGNED);
+  LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
+  const int G = C / 4;
+  const long long n = (long long)P * G;
+  LSS_REQUIRE(P > 0 && n < (1ll << 31), LSS_ERR_BAD_DIMENSION);
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  pool_dense_bwd_nhwc_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(d_dbev), d_cells, n, G, FastDiv(G),
+      reinterpret_cast<float4*>(d_dx));
+  LSS_LAUNCH_CHECK("pool_dense_bwd_nhwc_kernel");
+  return LSS_OK;
+}
+
+int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* shape,
+                   float* d_depth_t, float* d_feat_t, void* stream) {
+  LSS_REQUIRE(d_depth && d_feat && d_depth_t && d_feat_t, LSS_ERR_NULL_POINTER);
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  const int HW = shape->fH * shape->fW, BN = shape->B * shape->N;
+  const int R = shape->D > shape->C ? shape->D : shape->C;
+  LSS_REQUIRE(BN * 2 <= 65535, LSS_ERR_BAD_DIMENSION);
+  dim3 grid((HW + 31) / 32, (R + 31) / 32, BN * 2);
+  lift_stage_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_depth, d_feat, shape->D, shape->C, HW,
+                                                        d_depth_t, d_feat_t);
+  LSS_LAUNCH_CHECK("lift_stage_kernel");
+  return LSS_OK;
+}
+
+int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t,
+                      const int32_t* d_sorted_points, const int32_t* d_cell_range,
+                      const LssGrid* grid, const LssShape* shape, int32_t layout, float* d_bev,
+                      void* stream) {
+  LSS_REQUIRE(d_depth_t && d_feat_t, LSS_ERR_NULL_POINTER);
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  LSS_REQUIRE(aligned16(d_feat_t), LSS_ERR_MISALIGNED);
+  const int HW = shape->fH * shape->fW;
+  return pool_fwd_common(true, d_depth_t, d_feat_t, nullptr, d_sorted_points, d_cell_range, grid,
+                         shape->B, shape->C, shape->D, HW, (long long)shape->D * HW, layout, d_bev,
+                         as_stream(stream));
+}
+
+int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
+                      const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
+                      int32_t layout, float* d_ddepth, float* d_dfeat, void* stream) {
+  LSS_REQUIRE(d_dbev && d_depth_t && d_feat_t && d_cells && d_ddepth && d_dfeat, LSS_ERR_NULL_POINTER);
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  GridDev g;
+  rc = make_grid(grid, shape->B, &g);
+  if (rc) return rc;
+  LSS_REQUIRE(shape->C % 4 == 0 && aligned16(d_dbev) && aligned16(d_feat_t), LSS_ERR_MISALIGNED);
+  LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
+  PoolBwdArgs a;
+  a.dbev = reinterpret_cast<const float4*>(d_dbev); a.depth_t = d_depth_t;
+  a.feat_t = reinterpret_cast<const float4*>(d_feat_t); a.cells = d_cells;
+  a.ddepth = d_ddepth; a.dfeat = d_dfeat;
+  a.D = shape->D; a.fH = shape->fH; a.fW = shape->fW; a.C = shape->C; a.G = shape->C / 4;
+  const size_t smem = ((size_t)2 * a.D * a.fW + (size_t)a.C * (a.fW + 1)) * 4;
+  LSS_REQUIRE(smem <= 200 * 1024, LSS_ERR_UNSUPPORTED);
+  const int blocks = shape->B * shape->N * shape->fH;
+  cudaStream_t st = as_stream(stream);
+  const int G = a.G;
+  if (G <= 4) return launch_bwd<4, 1>(a, blocks, smem, st);
+  if (G <= 8) return launch_bwd<8, 1>(a, blocks, smem, st);
+  if (G <= 16) return launch_bwd<16, 1>(a, blocks, smem, st);
+  if (G <= 32) return launch_bwd<32, 1>(a, blocks, smem, st);
+  if (G <= 64) return launch_bwd<32, 2>(a, blocks, smem, st);
+  if (G <= 128) return launch_bwd<32, 4>(a, blocks, smem, st);
+  return LSS_ERR_UNSUPPORTED;
+}
+
+size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid) {
+  if (check_shape(shape) != LSS_OK) return 0;
+  GridDev g;
+  if (make_grid(grid, shape->B, &g) != LSS_OK) return 0;
+  const long long P = shape_points(shape);
+  const SortPlan s = make_sort_plan(P, g.n_cells);
+  return s.total_bytes + 2 * align_up((size_t)P * 4, 256);
+}
+
+int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
+                   const float* d_trans, const float* d_intrins, const float* d_post_rots,
+                   const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
+                   int32_t* d_cells, int32_t* d_sorted_points, int32_t* d_cell_range,
+                   int32_t* d_counts, void* d_workspace, size_t workspace_bytes, void* stream) {
+  LSS_REQUIRE(d_us && d_vs && d_ds && d_rots && d_trans && d_intrins && d_post_rots &&
+                  d_post_trans && d_cells && d_sorted_points && d_cell_range && d_counts &&
+                  d_workspace, LSS_ERR_NULL_POINTER);
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  GridDev g;
+  rc = make_grid(grid, shape->B, &g);
+  if (rc) return rc;
+  LSS_REQUIRE(aligned16(d_workspace), LSS_ERR_MISALIGNED);
+  const long long P = shape_points(shape);
+  const SortPlan s = make_sort_plan(P, g.n_cells);
+  const size_t need = s.total_bytes + 2 * align_up((size_t)P * 4, 256);
+  LSS_REQUIRE(workspace_bytes >= need, LSS_ERR_WORKSPACE_TOO_SMALL);
+  cudaStream_t st = as_stream(stream);
+  char* w = static_cast<char*>(d_workspace);
+  int32_t* ranks = reinterpret_cast<int32_t*>(w + s.total_bytes);
+  int32_t* sorted_ranks = reinterpret_cast<int32_t*>(w + s.total_bytes + align_up((size_t)P * 4, 256));
+
+  LSS_CUDA_TRY(cudaMemsetAsync(d_cell_range, 0, (size_t)g.n_cells * 8, st), "memset cell_range");
+  LSS_CUDA_TRY(cudaMemsetAsync(d_counts, 0, 8, st), "memset counts");
+
+  GeomArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.us = d_us; ga.vs = d_vs; ga.ds = d_ds;
+  ga.post_trans = d_post_trans; ga.trans = d_trans;
+  ga.rots = d_rots; ga.intrins = d_intrins; ga.post_rots = d_post_rots;
+  ga.raw = 1; ga.N = shape->N; ga.D = shape->D; ga.fH = shape->fH; ga.fW = shape->fW;
+  PointOut out{nullptr, nullptr, ranks, d_cells};
+  SortDigits sd = sort_digits(s, d_workspace);
+  rc = launch_geometry(ga, g, shape, out, &sd, st);
+  if (rc) return rc;
+  rc = run_sort_passes(s, ranks, sorted_ranks, d_sorted_points, P, d_workspace, st);
+  if (rc) return rc;
+  // K3 also wipes the sort's control words so the workspace is ready for the next call
+  return launch_intervals(sorted_ranks, P, g, nullptr, d_cell_range, d_counts,
+                          reinterpret_cast<uint32_t*>(w + s.off_control),
+                          (long long)(s.control_bytes / 4), st);
+}
+
+}  // extern "C"

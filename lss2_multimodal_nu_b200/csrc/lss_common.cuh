@@ -1,0 +1,117 @@
+// Shared helpers for the Lift-Splat sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "lss_b200.h"
+
+namespace lss {
+
+// ---- error plumbing -------------------------------------------------------
+char* cuda_error_buffer();  // thread-local, defined in lss_abi.cu
+
+inline int record_cuda_error(cudaError_t e, const char* where) {
+  snprintf(cuda_error_buffer(), 256, "%s: %s", where, cudaGetErrorString(e));
+  return LSS_ERR_CUDA;
+}
+
+#define LSS_LAUNCH_CHECK(where)                                     \
+  do {                                                              \
+    cudaError_t e__ = cudaGetLastError();                           \
+    if (e__ != cudaSuccess) return lss::record_cuda_error(e__, where); \
+  } while (0)
+
+#define LSS_CUDA_TRY(expr, where)                                   \
+  do {                                                              \
+    cudaError_t e__ = (expr);                                       \
+    if (e__ != cudaSuccess) return lss::record_cuda_error(e__, where); \
+  } while (0)
+
+#define LSS_REQUIRE(cond, status) \
+  do {                            \
+    if (!(cond)) return (status); \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;  // B200
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ---- division by a runtime constant ---------------------------------------
+// q = n / d for 0 <= n < 2^31, 1 <= d < 2^31:  q = (n * m) >> s with
+// s = 31 + ceil(log2 d), m = floor(2^s / d) + 1 (fits 32 bits).
+struct FastDiv {
+  uint32_t m, s, d;
+  FastDiv() : m(0), s(0), d(1) {}
+  explicit FastDiv(uint32_t div) : d(div) {
+    uint32_t L = 0;
+    while ((1ull << L) < div) ++L;
+    s = 31 + L;
+    m = static_cast<uint32_t>(((1ull << s) / div) + 1ull);
+  }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return static_cast<uint32_t>((static_cast<unsigned long long>(n) * m) >> s);
+#else
+    return static_cast<uint32_t>((static_cast<uint64_t>(n) * m) >> s);
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
+// ---- grid constants as kernels see them -----------------------------------
+struct GridDev {
+  float off[3];  // bx - dx/2   (reference src/model_baseline.py:92)
+  float dx[3];
+  float nxf[3];
+  int32_t nx[3];
+  int32_t B;
+  int32_t n_cells;  // nx0*nx1*nx2*B, also the sentinel rank
+};
+
+inline int make_grid(const LssGrid* g, int32_t B, GridDev* out) {
+  if (!g) return LSS_ERR_NULL_POINTER;
+  if (B <= 0) return LSS_ERR_BAD_DIMENSION;
+  int64_t cells = B;
+  for (int i = 0; i < 3; ++i) {
+    if (g->nx[i] <= 0 || g->nx[i] >= (1 << 24)) return LSS_ERR_BAD_DIMENSION;
+    cells *= g->nx[i];
+    // the same two float32 operations torch performs: (dx / 2.) then (bx - .)
+    volatile float half = g->dx[i] / 2.0f;
+    volatile float off = g->bx[i] - half;
+    out->off[i] = off;
+    out->dx[i] = g->dx[i];
+    out->nx[i] = g->nx[i];
+    out->nxf[i] = static_cast<float>(g->nx[i]);
+  }
+  if (cells >= 0x7fffffffLL) return LSS_ERR_BAD_DIMENSION;
+  out->B = B;
+  out->n_cells = static_cast<int32_t>(cells);
+  return LSS_OK;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
+
+// streaming 128-bit store: the BEV map is written once and not re-read by us
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v) { __stcs(p, v); }
+
+}  // namespace lss

@@ -1,0 +1,400 @@
+"""Host side of the Lift-Splat hot path: torch tensors in, C-ABI calls out.
+
+Every function here enqueues hand-written sm_100a kernels from liblss_b200.so on
+torch's current CUDA stream.  PyTorch supplies device memory, streams and
+autograd plumbing only; there is no CPU path and no PyTorch fallback -- a
+non-CUDA tensor raises.
+
+Mapping to the reference (paths relative to the reference root):
+  GridSpec            gen_dx_bx                     src/tools.py:172-178
+  camera_prep         torch.inverse / matmul        src/model_baseline.py:60,66
+  geometry            get_geometry                  src/model_baseline.py:50-70
+  quantize_rank       quantise, kept mask, ranks    src/model_baseline.py:92-109
+  sort_ranks          ranks.argsort()               src/model_baseline.py:110
+  intervals           QuickCumsum boundary mask     src/tools.py:196-197
+  build_plan          geometry half of get_voxels   src/model_baseline.py:128-131
+  lift_splat          lift + voxel_pooling fwd/bwd  src/modules.py:84,
+                                                    src/model_baseline.py:84-126,
+                                                    src/tools.py:192-218
+  pool_dense          voxel_pooling on a dense x    src/model_baseline.py:84-126
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _abi
+
+
+# --------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "lss2_multimodal_nu_b200: tensor on %s -- this path runs only on CUDA "
+                "(sm_100a kernels); there is no CPU fallback" % t.device)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("tensors on different devices: %s vs %s" % (dev, t.device))
+    return dev
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """float32 + contiguous (no copy when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+@dataclass(frozen=True)
+class GridSpec:
+    """Host copy of the grid constants gen_dx_bx produces."""
+    dx: Tuple[float, float, float]
+    bx: Tuple[float, float, float]
+    nx: Tuple[int, int, int]
+
+    @staticmethod
+    def from_bounds(xbound, ybound, zbound) -> "GridSpec":
+        # same arithmetic as reference src/tools.py:173-175; torch.Tensor(...) rounds
+        # the python floats to float32
+        rows = [xbound, ybound, zbound]
+        dx = torch.tensor([r[2] for r in rows], dtype=torch.float64).float().tolist()
+        bx = torch.tensor([r[0] + r[2] / 2.0 for r in rows], dtype=torch.float64).float().tolist()
+        nx = [int((r[1] - r[0]) / r[2]) for r in rows]
+        return GridSpec(tuple(dx), tuple(bx), tuple(nx))
+
+    @staticmethod
+    def from_tensors(dx, bx, nx) -> "GridSpec":
+        """From the module's dx/bx/nx parameters (one device->host read; cache the result)."""
+        return GridSpec(tuple(float(v) for v in dx.detach().cpu().tolist()),
+                        tuple(float(v) for v in bx.detach().cpu().tolist()),
+                        tuple(int(v) for v in nx.detach().cpu().tolist()))
+
+    def c(self) -> _abi.LssGrid:
+        return _abi.make_grid(self.dx, self.bx, self.nx)
+
+    def n_cells(self, B: int) -> int:
+        return self.nx[0] * self.nx[1] * self.nx[2] * B
+
+
+def frustum_axes(frustum: torch.Tensor):
+    """(us[fW], vs[fH], ds[D]) from the module's (D,fH,fW,3) frustum parameter
+    (reference src/model_baseline.py:41-47): the frustum is the outer product of
+    these three tables, so they carry its exact bits."""
+    us = frustum[0, 0, :, 0].detach().float().contiguous()
+    vs = frustum[0, :, 0, 1].detach().float().contiguous()
+    ds = frustum[:, 0, 0, 2].detach().float().contiguous()
+    return us, vs, ds
+
+
+# --------------------------------------------------------------------------
+# K0 / K1 / K1' / K2 / K3 as individual operators (parity surface)
+# --------------------------------------------------------------------------
+def camera_prep(rots, intrins, post_rots):
+    """inverse(post_rots), rots @ inverse(intrins) -- (..., 3, 3) float32 each."""
+    dev = _need_cuda(rots, intrins, post_rots)
+    rots, intrins, post_rots = _f32c(rots), _f32c(intrins), _f32c(post_rots)
+    n = rots.numel() // 9
+    ipr = torch.empty_like(post_rots)
+    comb = torch.empty_like(rots)
+    _abi.call("lss_camera_prep", _ptr(rots), _ptr(intrins), _ptr(post_rots), n, _ptr(ipr),
+              _ptr(comb), _stream(dev))
+    return ipr, comb
+
+
+def geometry(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: GridSpec,
+             inv_post_rots=None, combine=None, want_geom=True, want_coords=False,
+             want_kept=False) -> Dict[str, torch.Tensor]:
+    """Fused frustum geometry -> rank.  Returns a dict with 'ranks' (P) int32,
+    'cells' (P) int32 and, on request, 'geom' (B,N,D,fH,fW,3), 'coords' (P,3)
+    int32, 'kept' (P) uint8.  ``inv_post_rots`` / ``combine`` override K0."""
+    dev = _need_cuda(us, vs, ds, rots, trans, intrins, post_rots, post_trans)
+    B, N = trans.shape[0], trans.shape[1]
+    D, fH, fW = ds.numel(), vs.numel(), us.numel()
+    if inv_post_rots is None or combine is None:
+        ipr, comb = camera_prep(rots, intrins, post_rots)
+        inv_post_rots = ipr if inv_post_rots is None else inv_post_rots
+        combine = comb if combine is None else combine
+    P = B * N * D * fH * fW
+    shape = _abi.make_shape(B, N, D, fH, fW, 4)
+    out = {"ranks": torch.empty(P, dtype=torch.int32, device=dev),
+           "cells": torch.empty(P, dtype=torch.int32, device=dev)}
+    if want_geom:
+        out["geom"] = torch.empty((B, N, D, fH, fW, 3), dtype=torch.float32, device=dev)
+    if want_coords:
+        out["coords"] = torch.empty((P, 3), dtype=torch.int32, device=dev)
+    if want_kept:
+        out["kept"] = torch.empty(P, dtype=torch.uint8, device=dev)
+    g = grid.c()
+    _abi.call("lss_geometry_rank", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
+              _ptr(_f32c(inv_post_rots)), _ptr(_f32c(post_trans)), _ptr(_f32c(combine)),
+              _ptr(_f32c(trans)), g, shape, _ptr(out.get("geom")), _ptr(out.get("coords")),
+              _ptr(out.get("kept")), _ptr(out["ranks"]), _ptr(out["cells"]), _stream(dev))
+    return out
+
+
+def quantize_rank(geom: torch.Tensor, grid: GridSpec, B: int, want_coords=False,
+                  want_kept=False) -> Dict[str, torch.Tensor]:
+    """Quantise a dense geometry tensor (..., 3) whose leading dim is the batch."""
+    dev = _need_cuda(geom)
+    geom = _f32c(geom)
+    P = geom.numel() // 3
+    out = {"ranks": torch.empty(P, dtype=torch.int32, device=dev),
+           "cells": torch.empty(P, dtype=torch.int32, device=dev)}
+    if want_coords:
+        out["coords"] = torch.empty((P, 3), dtype=torch.int32, device=dev)
+    if want_kept:
+        out["kept"] = torch.empty(P, dtype=torch.uint8, device=dev)
+    _abi.call("lss_quantize_rank", _ptr(geom), grid.c(), B, P, _ptr(out.get("coords")),
+              _ptr(out.get("kept")), _ptr(out["ranks"]), _ptr(out["cells"]), _stream(dev))
+    return out
+
+
+def sort_ranks(ranks: torch.Tensor, n_cells: int):
+    """Stable sort of int32 ranks -> (sorted_ranks, sorted_points)."""
+    dev = _need_cuda(ranks)
+    assert ranks.dtype == torch.int32 and ranks.is_contiguous()
+    P = ranks.numel()
+    nbytes = _abi.load().lss_sort_workspace_bytes(P, n_cells)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    sk = torch.empty_like(ranks)
+    sp = torch.empty_like(ranks)
+    _abi.call("lss_sort_ranks", _ptr(ranks), P, n_cells, _ptr(sk), _ptr(sp), _ptr(ws), nbytes,
+              _stream(dev))
+    return sk, sp
+
+
+def intervals(sorted_ranks: torch.Tensor, grid: GridSpec, B: int, want_last_mask=False):
+    """Run detection -> (cell_range (n_cells,2) int32, counts (2) int32 [K, V], last_mask|None)."""
+    dev = _need_cuda(sorted_ranks)
+    P = sorted_ranks.numel()
+    cell_range = torch.zeros((grid.n_cells(B), 2), dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    last = torch.empty(P, dtype=torch.uint8, device=dev) if want_last_mask else None
+    _abi.call("lss_intervals", _ptr(sorted_ranks), P, grid.c(), B, _ptr(last), _ptr(cell_range),
+              _ptr(counts), _stream(dev))
+    return cell_range, counts, last
+
+
+# --------------------------------------------------------------------------
+# the plan: everything that depends only on the calibration
+# --------------------------------------------------------------------------
+@dataclass
+class Plan:
+    """Per-batch index tables: depends on calibration + grid only, never on features."""
+    grid: GridSpec
+    B: int
+    N: int
+    D: int
+    fH: int
+    fW: int
+    cells: torch.Tensor          # (P) int32 output cell of each point, -1 if dropped
+    sorted_points: torch.Tensor  # (P) int32 point index in rank order (kept points first)
+    cell_range: torch.Tensor     # (n_cells, 2) int32 [start, end) into sorted_points
+    counts: torch.Tensor         # (2) int32 {K, V}
+
+    @property
+    def P(self) -> int:
+        return self.B * self.N * self.D * self.fH * self.fW
+
+    def shape(self, C: int) -> _abi.LssShape:
+        return _abi.make_shape(self.B, self.N, self.D, self.fH, self.fW, C)
+
+
+_WORKSPACES: Dict[Tuple, torch.Tensor] = {}
+
+
+def _plan_workspace(dev, stream: int, shape: _abi.LssShape, g: _abi.LssGrid) -> torch.Tensor:
+    """Zero-initialised scratch, reused per (device, stream, problem size)."""
+    nbytes = _abi.load().lss_plan_workspace_bytes(shape, g)
+    if nbytes == 0:
+        raise RuntimeError("lss_plan_workspace_bytes rejected the shape/grid")
+    key = (dev.index, stream, nbytes)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def build_plan(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: GridSpec) -> Plan:
+    """K0 -> K1' -> K2 -> K3 in one C call (lss_build_plan)."""
+    dev = _need_cuda(us, vs, ds, rots, trans, intrins, post_rots, post_trans)
+    B, N = trans.shape[0], trans.shape[1]
+    D, fH, fW = ds.numel(), vs.numel(), us.numel()
+    shape = _abi.make_shape(B, N, D, fH, fW, 4)
+    g = grid.c()
+    P = B * N * D * fH * fW
+    st = _stream(dev)
+    ws = _plan_workspace(dev, st, shape, g)
+    cells = torch.empty(P, dtype=torch.int32, device=dev)
+    sorted_points = torch.empty(P, dtype=torch.int32, device=dev)
+    cell_range = torch.empty((grid.n_cells(B), 2), dtype=torch.int32, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    try:
+        _abi.call("lss_build_plan", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
+                  _ptr(_f32c(rots)), _ptr(_f32c(trans)), _ptr(_f32c(intrins)),
+                  _ptr(_f32c(post_rots)), _ptr(_f32c(post_trans)), g, shape, _ptr(cells),
+                  _ptr(sorted_points), _ptr(cell_range), _ptr(counts), _ptr(ws), ws.numel(), st)
+    except _abi.LssError:
+        ws.zero_()  # a failed call may leave the control words dirty
+        raise
+    return Plan(grid, B, N, D, fH, fW, cells, sorted_points, cell_range, counts)
+
+
+def plan_from_geom(geom: torch.Tensor, grid: GridSpec) -> Plan:
+    """Plan from a dense (B,N,D,fH,fW,3) geometry tensor (the literal
+    voxel_pooling(geom_feats, x) signature): K1 -> K2 -> K3."""
+    B, N, D, fH, fW, _ = geom.shape
+    q = quantize_rank(geom, grid, B)
+    sk, sp = sort_ranks(q["ranks"], grid.n_cells(B))
+    cell_range, counts, _ = intervals(sk, grid, B)
+    return Plan(grid, B, N, D, fH, fW, q["cells"], sp, cell_range, counts)
+
+
+# --------------------------------------------------------------------------
+# BEV tensor layout helpers
+# --------------------------------------------------------------------------
+def _alloc_bev(plan: Plan, C: int, dev) -> torch.Tensor:
+    """(B, X, Y, Z*C) storage; .permute(0,3,1,2) is the logical (B, C*Z, X, Y) result
+    with channels_last strides."""
+    X, Y, Z = plan.grid.nx
+    return torch.empty((plan.B, X, Y, Z * C), dtype=torch.float32, device=dev)
+
+
+def _as_nhwc(grad: torch.Tensor) -> torch.Tensor:
+    """View/copy of a logical (B, C, X, Y) tensor as contiguous (B, X, Y, C)."""
+    g = grad.permute(0, 2, 3, 1)
+    if g.dtype != torch.float32:
+        g = g.float()
+    return g if g.is_contiguous() else g.contiguous()
+
+
+# --------------------------------------------------------------------------
+# fused lift + splat (K4 / K5)
+# --------------------------------------------------------------------------
+def lift_stage(depth: torch.Tensor, feat: torch.Tensor, plan: Plan):
+    """Pixel-major staging copies (B*N*fH*fW, D) and (B*N*fH*fW, C)."""
+    dev = _need_cuda(depth, feat)
+    depth, feat = _f32c(depth), _f32c(feat)
+    BN, C = feat.shape[0], feat.shape[1]
+    HW = plan.fH * plan.fW
+    depth_t = torch.empty((BN * HW, plan.D), dtype=torch.float32, device=dev)
+    feat_t = torch.empty((BN * HW, C), dtype=torch.float32, device=dev)
+    _abi.call("lss_lift_stage", _ptr(depth), _ptr(feat), plan.shape(C), _ptr(depth_t),
+              _ptr(feat_t), _stream(dev))
+    return depth_t, feat_t
+
+
+class _LiftSplat(torch.autograd.Function):
+    """Counterpart of QuickCumsum (reference src/tools.py:192-218) for the fused op:
+    forward saves the staged inputs and the per-point cell table, index tensors
+    are non-differentiable, backward is one kernel."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, plan: Plan):
+        dev = _need_cuda(depth, feat)
+        BN, C = feat.shape[0], feat.shape[1]
+        if C % 4 != 0:
+            raise RuntimeError("C must be a multiple of 4 (128-bit channel vectors), got %d" % C)
+        if tuple(depth.shape) != (plan.B * plan.N, plan.D, plan.fH, plan.fW) or \
+                tuple(feat.shape[2:]) != (plan.fH, plan.fW) or BN != plan.B * plan.N:
+            raise RuntimeError("depth %s / feat %s do not match the plan (B=%d N=%d D=%d fH=%d fW=%d)"
+                               % (tuple(depth.shape), tuple(feat.shape), plan.B, plan.N, plan.D,
+                                  plan.fH, plan.fW))
+        depth_t, feat_t = lift_stage(depth, feat, plan)
+        bev = _alloc_bev(plan, C, dev)
+        _abi.call("lss_liftsplat_fwd", _ptr(depth_t), _ptr(feat_t), _ptr(plan.sorted_points),
+                  _ptr(plan.cell_range), plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC,
+                  _ptr(bev), _stream(dev))
+        ctx.plan = plan
+        ctx.C = C
+        ctx.in_dtypes = (depth.dtype, feat.dtype)
+        ctx.save_for_backward(depth_t, feat_t)
+        return bev.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        depth_t, feat_t = ctx.saved_tensors
+        plan, C = ctx.plan, ctx.C
+        dev = grad_bev.device
+        g = _as_nhwc(grad_bev)
+        ddepth = torch.empty((plan.B * plan.N, plan.D, plan.fH, plan.fW), dtype=torch.float32, device=dev)
+        dfeat = torch.empty((plan.B * plan.N, C, plan.fH, plan.fW), dtype=torch.float32, device=dev)
+        _abi.call("lss_liftsplat_bwd", _ptr(g), _ptr(depth_t), _ptr(feat_t), _ptr(plan.cells),
+                  plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC, _ptr(ddepth), _ptr(dfeat),
+                  _stream(dev))
+        return ddepth.to(ctx.in_dtypes[0]), dfeat.to(ctx.in_dtypes[1]), None
+
+
+def lift_splat(depth: torch.Tensor, feat: torch.Tensor, plan: Plan,
+               memory_format: torch.memory_format = torch.channels_last) -> torch.Tensor:
+    """BEV (B, C*Z, X, Y) float32 = splat(lift(depth, feat)).
+
+    depth (B*N, D, fH, fW) is the per-pixel depth distribution, feat
+    (B*N, C, fH, fW) the context features; the (B*N, C, D, fH, fW) product of
+    reference src/modules.py:84 is never materialised.  The result has
+    channels_last strides by default (each voxel's C values are one contiguous
+    line); pass torch.contiguous_format for the reference's dense NCHW layout
+    (one extra transpose pass)."""
+    out = _LiftSplat.apply(depth, feat, plan)
+    if memory_format == torch.contiguous_format:
+        out = out.contiguous()
+    return out
+
+
+# --------------------------------------------------------------------------
+# dense pooling (K4a / K5a): voxel_pooling on a materialised frustum tensor
+# --------------------------------------------------------------------------
+class _PoolDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, plan: Plan):
+        dev = _need_cuda(x)
+        C = x.shape[-1]
+        if C % 4 != 0:
+            raise RuntimeError("C must be a multiple of 4, got %d" % C)
+        x2 = _f32c(x.reshape(-1, C))
+        if x2.shape[0] != plan.P:
+            raise RuntimeError("x has %d points, plan has %d" % (x2.shape[0], plan.P))
+        bev = _alloc_bev(plan, C, dev)
+        _abi.call("lss_pool_dense_fwd", _ptr(x2), _ptr(plan.sorted_points), _ptr(plan.cell_range),
+                  plan.grid.c(), plan.B, C, _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
+        ctx.plan = plan
+        ctx.x_shape = tuple(x.shape)
+        ctx.x_dtype = x.dtype
+        return bev.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        plan = ctx.plan
+        C = ctx.x_shape[-1]
+        g = _as_nhwc(grad_bev)
+        dx = torch.empty((plan.P, C), dtype=torch.float32, device=grad_bev.device)
+        _abi.call("lss_pool_dense_bwd", _ptr(g), _ptr(plan.cells), plan.grid.c(), plan.B, C,
+                  plan.P, _abi.LSS_BEV_NHWC, _ptr(dx), _stream(grad_bev.device))
+        return dx.view(ctx.x_shape).to(ctx.x_dtype), None
+
+
+def pool_dense(x: torch.Tensor, plan: Plan,
+               memory_format: torch.memory_format = torch.channels_last) -> torch.Tensor:
+    """voxel_pooling for a materialised (B,N,D,fH,fW,C) tensor (any strides)."""
+    out = _PoolDense.apply(x, plan)
+    if memory_format == torch.contiguous_format:
+        out = out.contiguous()
+    return out

@@ -1,0 +1,34 @@
+"""Run an unmodified reference script with the B200 hot path installed.
+
+    python -m lss2_multimodal_nu_b200.run train.py --dataroot ... --bsize 8
+    python -m lss2_multimodal_nu_b200.run predict.py ...
+
+The script's directory is put on sys.path (so ``from src... import`` resolves as
+it does when the script is run directly), the reference classes are patched
+(patch.install_reference_classes) and the script is executed with runpy as
+``__main__``.  The reference files are not touched.
+"""
+import os
+import runpy
+import sys
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        print(__doc__)
+        return 2
+    script = os.path.abspath(argv[0])
+    sys.path.insert(0, os.path.dirname(script))
+    from . import patch
+    n = patch.install_reference_classes()
+    if n == 0:
+        print("lss2_multimodal_nu_b200.run: no reference model classes found next to %s" % script,
+              file=sys.stderr)
+    sys.argv = [script] + argv[1:]
+    runpy.run_path(script, run_name="__main__")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
