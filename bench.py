@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Headline benchmark: BEV pooled samples/sec (6 cams, fwd+bwd), BASELINE.json config 2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config config2]
+
+One "step" = one batch (B=8 samples x 6 cameras, 128x352, D=41, C=64, 200x200x1
+BEV) through the whole hot path, forward + backward:
+    camera prep + frustum geometry -> ranks -> radix sort -> intervals   (lss_build_plan)
+    lift staging -> fused lift+splat forward                            (lss_lift_stage, lss_liftsplat_fwd)
+    fused backward                                                       (lss_liftsplat_bwd)
+`value`   device-resident inputs, every step replayed as a CUDA graph of the C-ABI calls.
+`e2e`     the public Python API (functional.build_plan + lift_splat autograd) fed from pinned
+          HOST buffers: H2D of depth/feat/calibration and D2H of the gradients every step.
+`roofline` the dominant kernel (fused forward: it writes the whole BEV map), timed alone with CUDA
+          events, algorithmic bytes fwd = in + bev.
+`cpu_baseline` / `--impl reference`: the C restatement of the reference's algorithm
+          (oracle/lss_oracle.c, "port") on the host cores.
+Multi-GPU: the batch shards by sample, one process per GPU, no data-path collective
+(weak scaling); timing = max over ranks of the CUDA-event time.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="config2")
+    ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 100)")
+    return ap.parse_args()
+
+
+METRIC = "BEV pooled samples/sec (6 cams, fwd+bwd)"
+UNIT = "samples/s"
+
+
+def workload_name(cfg):
+    return ("LSS voxel_pooling fwd+bwd, batch %d/GPU, %d cams %dx%d, D=%d, C=%d, %dx%dx%d BEV"
+            % (cfg.B, cfg.N, cfg.final_dim[0], cfg.final_dim[1], cfg.D, cfg.C, *cfg.nx))
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ---------------------------------------------------------------------------
+def cpu_port_run(cfg, steps, warmup, budget_s=None):
+    """Time the C restatement of the reference's algorithm (geometry + lift + voxel_pooling
+    fwd + bwd) on one batch of the workload with all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import c_oracle as CO
+    import lss_oracle as O
+    from lss2_multimodal_nu_b200 import synthetic as S
+    cal = S.make_calibration(cfg); ft = S.make_features(cfg); dbev = S.make_dbev(cfg)
+    us, vs, ds = O.frustum_axes(cfg.final_dim, cfg.downsample, cfg.dbound)
+    dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    cores = CO.threads()
+
+    def one():
+        geom = CO.geometry(us, vs, ds, **cal)
+        return CO.step(ft["depth"], ft["feat"], geom, dbev, dx, bx, nx, cfg.B, cfg.N, mode=0)
+
+    for _ in range(max(1, warmup)):
+        one()
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s:
+            break
+    mean = float(np.mean(times))
+    return {"samples_per_s": cfg.B / mean, "ms_per_step": mean * 1e3, "cores": cores,
+            "steps": len(times)}
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    steps = max(1, min(args.steps, 40))
+    r = cpu_port_run(cfg, steps, min(args.warmup, 2), budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["samples_per_s"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 2),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "global_batch": cfg.B},
+        "cpu_baseline": {"value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": "one batch of %d samples per step, %d steps: C restatement of the "
+                                   "reference algorithm (oracle/lss_oracle.c), OpenMP" % (cfg.B, r["steps"])},
+        "e2e": {"value": r["samples_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the GPU works."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+        except Exception:
+            self.N = None
+
+    def sample(self):
+        if self.N is None:
+            return
+        N = self.N
+        try:
+            self.samples.append(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
+            try:
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def start(self, period=0.002):
+        def loop():
+            while not self._stop.is_set():
+                self.sample()
+                time.sleep(period)
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lss2_multimodal_nu_b200 import _abi, functional as F, synthetic as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _abi.load()
+
+    # ---- per-rank inputs: `sets` independent batches so the working set exceeds L2 -------
+    grid = F.GridSpec.from_bounds(cfg.xbound, cfg.ybound, cfg.zbound)
+    frustum_t = None
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lss_oracle as O   # only for the frustum axes tables + cpu_baseline (never timed as product)
+    us, vs, ds = (torch.from_numpy(a).to(dev) for a in O.frustum_axes(cfg.final_dim, cfg.downsample, cfg.dbound))
+    X, Y, Z = grid.nx
+    C = cfg.C
+    shape = _abi.make_shape(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, C)
+    g = grid.c()
+    P = cfg.P
+    BN, HW = cfg.B * cfg.N, cfg.fH * cfg.fW
+    host, sets = [], []
+    for s in range(args.sets):
+        seed = 1234 + 1000 * rank + s
+        cal = S.make_calibration(cfg, seed); ft = S.make_features(cfg, seed)
+        h = {k: torch.from_numpy(v).pin_memory() for k, v in {**cal, **ft}.items()}
+        host.append(h)
+        d = {k: v.to(dev) for k, v in h.items()}
+        gen = torch.Generator(device=dev); gen.manual_seed(seed)
+        d["dbev"] = torch.randn((cfg.B, X, Y, Z * C), device=dev, generator=gen)   # channels-innermost
+        d["cells"] = torch.empty(P, dtype=torch.int32, device=dev)
+        d["sorted_points"] = torch.empty(P, dtype=torch.int32, device=dev)
+        d["cell_range"] = torch.empty((grid.n_cells(cfg.B), 2), dtype=torch.int32, device=dev)
+        d["counts"] = torch.empty(2, dtype=torch.int32, device=dev)
+        d["depth_t"] = torch.empty((BN * HW, cfg.D), device=dev)
+        d["feat_t"] = torch.empty((BN * HW, C), device=dev)
+        d["bev"] = torch.empty((cfg.B, X, Y, Z * C), device=dev)
+        d["ddepth"] = torch.empty((BN, cfg.D, cfg.fH, cfg.fW), device=dev)
+        d["dfeat"] = torch.empty((BN, C, cfg.fH, cfg.fW), device=dev)
+        sets.append(d)
+    ws_bytes = _abi.load().lss_plan_workspace_bytes(shape, g)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+    p = lambda t: t.data_ptr()
+
+    def k_plan(d, st):
+        _abi.call("lss_build_plan", p(us), p(vs), p(ds), p(d["rots"]), p(d["trans"]), p(d["intrins"]),
+                  p(d["post_rots"]), p(d["post_trans"]), g, shape, p(d["cells"]), p(d["sorted_points"]),
+                  p(d["cell_range"]), p(d["counts"]), p(ws), ws_bytes, st)
+
+    def k_stage(d, st):
+        _abi.call("lss_lift_stage", p(d["depth"]), p(d["feat"]), shape, p(d["depth_t"]), p(d["feat_t"]), st)
+
+    def k_fwd(d, st):
+        _abi.call("lss_liftsplat_fwd", p(d["depth_t"]), p(d["feat_t"]), p(d["sorted_points"]),
+                  p(d["cell_range"]), g, shape, _abi.LSS_BEV_NHWC, p(d["bev"]), st)
+
+    def k_bwd(d, st):
+        _abi.call("lss_liftsplat_bwd", p(d["dbev"]), p(d["depth_t"]), p(d["feat_t"]), p(d["cells"]), g,
+                  shape, _abi.LSS_BEV_NHWC, p(d["ddepth"]), p(d["dfeat"]), st)
+
+    def step(d, st):
+        k_plan(d, st); k_stage(d, st); k_fwd(d, st); k_bwd(d, st)
+
+    KERNELS_PER_STEP = 4 + 1 + 1 + 1   # geometry, 2 sort passes, intervals | stage | fwd | bwd
+
+    stream = torch.cuda.Stream(dev)
+    graphs = None
+    with torch.cuda.stream(stream):
+        st = stream.cuda_stream
+        for d in sets:                      # un-captured warm run (module load, attribute setup)
+            step(d, st)
+        stream.synchronize()
+        if not args.no_graph:
+            graphs = []
+            for d in sets:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=stream):
+                    step(d, torch.cuda.current_stream().cuda_stream)
+                graphs.append(gr)
+
+        def run_step(i):
+            if graphs is not None:
+                graphs[i % len(graphs)].replay()
+            else:
+                step(sets[i % len(sets)], st)
+
+        def barrier():
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for i in range(max(3, args.warmup)):
+            run_step(i)
+        barrier()
+        clocks = ClockSampler(local)
+        clocks.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            run_step(i)
+        e1.record(stream)
+        stream.synchronize()
+        clocks.stop()
+        elapsed_ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([elapsed_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t.item())
+        ms_per_step = elapsed_ms / args.steps
+        value = world * cfg.B * args.steps / (elapsed_ms * 1e-3)
+
+        # ---- per-kernel timing (CUDA events on the launching stream), cold rotating sets ----
+        def time_kernel(fn, n):
+            evs = []
+            for i in range(n):
+                d = sets[i % len(sets)]
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record(stream); fn(d, st); b.record(stream)
+                evs.append((a, b))
+            stream.synchronize()
+            ts = sorted(a.elapsed_time(b) for a, b in evs)
+            return {"mean_us": 1e3 * sum(ts) / len(ts), "median_us": 1e3 * ts[len(ts) // 2], "min_us": 1e3 * ts[0]}
+
+        n_k = min(args.steps, 200)
+        kt = {"plan": time_kernel(k_plan, n_k), "stage": time_kernel(k_stage, n_k),
+              "fwd": time_kernel(k_fwd, n_k), "bwd": time_kernel(k_bwd, n_k)}
+
+    # ---- roofline of the dominant kernel (fused forward) -----------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak = float(json.load(f)["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    alg = cfg.algorithmic_bytes()
+    fwd_s = kt["fwd"]["mean_us"] * 1e-6
+    achieved = alg["fwd"] / fwd_s / 1e9
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        try:
+            with open(tr_path) as f:
+                traffic = json.load(f).get(cfg.name, {}).get("fwd_dram_bytes")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "pool_fwd_nhwc_kernel<fused> (lss_liftsplat_fwd)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg["fwd"],
+                "kernel_us": kt["fwd"]["mean_us"], "peak_source": peak_src,
+                "step_frac_of_hbm_roofline": (alg["total"] / (ms_per_step * 1e-3) / 1e9) / peak,
+                "kernels_us": {k: round(v["mean_us"], 2) for k, v in kt.items()}}
+
+    # ---- e2e: public API, host buffers ----------------------------------------------------
+    e2e_steps = args.e2e_steps or min(args.steps, 100)
+    hb = sum(v.numel() * v.element_size() for v in host[0].values())
+    out_host = [(torch.empty((BN, cfg.D, cfg.fH, cfg.fW)).pin_memory(),
+                 torch.empty((BN, C, cfg.fH, cfg.fW)).pin_memory()) for _ in range(2)]
+    db = sum(t.numel() * t.element_size() for t in out_host[0])
+    CAL = ("rots", "trans", "intrins", "post_rots", "post_trans")
+
+    def e2e_step(i):
+        h = host[i % len(host)]
+        dbev = sets[i % len(sets)]["dbev"].permute(0, 3, 1, 2)   # produced on device by the downstream net
+        t = {k: h[k].to(dev, non_blocking=True) for k in h}
+        depth = t["depth"].requires_grad_(True); feat = t["feat"].requires_grad_(True)
+        plan = F.build_plan(us, vs, ds, *(t[k] for k in CAL), grid)
+        bev = F.lift_splat(depth, feat, plan)
+        bev.backward(dbev)
+        o = out_host[i % 2]
+        o[0].copy_(depth.grad, non_blocking=True); o[1].copy_(feat.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the step's result is on the host
+
+    for i in range(3):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": world * cfg.B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hb,
+           "d2h_bytes_per_step": db, "steps": e2e_steps,
+           "note": "public API (build_plan + lift_splat autograd), pinned host depth/feat/calibration in, "
+                   "d_depth/d_feat out, per-step stream sync; upstream dBEV stays on the device"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "global_batch": cfg.B * world,
+                   "parallelism": "sample-sharded x%d, no collective" % world,
+                   "bev_layout": "channels_last (NHWC storage of the logical (B,C*Z,X,Y) map)",
+                   "l2": "inputs larger than L2: %d rotating batch sets (%.0f MB BEV+dBEV each)"
+                         % (args.sets, 2 * alg["bev"] / 1e6),
+                   "launch": "cuda-graph replay" if graphs is not None else "stream launches",
+                   "step": "camera prep+geometry+sort+intervals, lift staging, fused fwd, fused bwd"},
+        "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_run(cfg, steps=60, warmup=1, budget_s=12.0)
+        line["cpu_baseline"] = {"value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": "%d steps of one %d-sample batch (C restatement of the reference "
+                                          "algorithm, oracle/lss_oracle.c, OpenMP)" % (r["steps"], cfg.B)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from lss2_multimodal_nu_b200 import synthetic as S
+    cfg = S.config(args.config)
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()
