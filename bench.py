@@ -210,6 +210,7 @@ def run_ours(args, cfg):
         d["dbev"] = torch.randn((cfg.B, X, Y, Z * C), device=dev, generator=gen)   # channels-innermost
         d["cells"] = torch.empty(P, dtype=torch.int32, device=dev)
         d["sorted_points"] = torch.empty(P, dtype=torch.int32, device=dev)
+        d["sorted_cells"] = torch.empty(P, dtype=torch.int32, device=dev)
         d["cell_range"] = torch.empty((grid.n_cells(cfg.B), 2), dtype=torch.int32, device=dev)
         d["counts"] = torch.empty(2, dtype=torch.int32, device=dev)
         d["depth_t"] = torch.empty((BN * HW, cfg.D), device=dev)
@@ -225,14 +226,15 @@ def run_ours(args, cfg):
     def k_plan(d, st):
         _abi.call("lss_build_plan", p(us), p(vs), p(ds), p(d["rots"]), p(d["trans"]), p(d["intrins"]),
                   p(d["post_rots"]), p(d["post_trans"]), g, shape, p(d["cells"]), p(d["sorted_points"]),
-                  p(d["cell_range"]), p(d["counts"]), p(ws), ws_bytes, st)
+                  p(d["sorted_cells"]), p(d["cell_range"]), p(d["counts"]), p(ws), ws_bytes, st)
 
     def k_stage(d, st):
         _abi.call("lss_lift_stage", p(d["depth"]), p(d["feat"]), shape, p(d["depth_t"]), p(d["feat_t"]), st)
 
     def k_fwd(d, st):
         _abi.call("lss_liftsplat_fwd", p(d["depth_t"]), p(d["feat_t"]), p(d["sorted_points"]),
-                  p(d["cell_range"]), g, shape, _abi.LSS_BEV_NHWC, p(d["bev"]), st)
+                  p(d["sorted_cells"]), p(d["cell_range"]), p(d["counts"]), g, shape,
+                  _abi.LSS_BEV_NHWC, p(d["bev"]), st)
 
     def k_bwd(d, st):
         _abi.call("lss_liftsplat_bwd", p(d["dbev"]), p(d["depth_t"]), p(d["feat_t"]), p(d["cells"]), g,

@@ -131,25 +131,29 @@ int lss_sort_ranks(const int32_t* d_ranks, int64_t P, int32_t n_cells, int32_t* 
  *     difference (:195,:200) needed it for.
  *     d_last_mask   (P) uint8, 1 at the last point of each run of equal ranks,
  *                   0 beyond the K kept points                    [optional]
+ *     d_sorted_cells (P) int32 output cell ((b*X+x)*Y+y)*Z+z of each sorted point
+ *                   (first K entries valid)                        [optional]
  *     d_cell_range  (n_cells,2) int32 [start, end) of every output cell's run in
- *                   the sorted order, indexed by OUTPUT cell ((b*X+x)*Y+y)*Z+z;
- *                   must be zero-filled by the caller (empty cells stay 0,0)
+ *                   the sorted order, indexed by OUTPUT cell; start >= end means
+ *                   empty; must be zero-filled by the caller
  *     d_counts      (2) int32: {K kept points, V occupied cells}; zero-filled
  *                   by the caller
  * ------------------------------------------------------------------------- */
 int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid, int32_t B,
-                  uint8_t* d_last_mask, int32_t* d_cell_range, int32_t* d_counts, void* stream);
+                  uint8_t* d_last_mask, int32_t* d_sorted_cells, int32_t* d_cell_range,
+                  int32_t* d_counts, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K4a dense pooling.  Replaces x[kept][sorts] -> QuickCumsum -> zeros ->
  *     index_put -> cat(unbind) (src/model_baseline.py:102-124) for a
  *     materialised frustum tensor d_x (P,C).  Every output element is written
- *     (zeros for empty voxels); d_bev is (B, C*Z, X, Y) in `layout`.
+ *     (zeros for empty voxels); d_bev is (B, C*Z, X, Y) in `layout`.  C <= 128.
  *     Backward (QuickCumsum.backward src/tools.py:211-218 + index backward):
  *     d_dx[p,:] = d_dbev[cell(p),:] for kept points, 0 otherwise.
  * ------------------------------------------------------------------------- */
 int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points,
-                       const int32_t* d_cell_range, const LssGrid* grid, int32_t B, int32_t C,
+                       const int32_t* d_sorted_cells, const int32_t* d_cell_range,
+                       const int32_t* d_counts, const LssGrid* grid, int32_t B, int32_t C,
                        int32_t layout, float* d_bev, void* stream);
 int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGrid* grid,
                        int32_t B, int32_t C, int64_t P, int32_t layout, float* d_dx,
@@ -176,9 +180,9 @@ int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* sh
  *     gather, as QuickCumsum.backward is); points that were dropped contribute 0.
  * ------------------------------------------------------------------------- */
 int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t,
-                      const int32_t* d_sorted_points, const int32_t* d_cell_range,
-                      const LssGrid* grid, const LssShape* shape, int32_t layout, float* d_bev,
-                      void* stream);
+                      const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
+                      const int32_t* d_cell_range, const int32_t* d_counts, const LssGrid* grid,
+                      const LssShape* shape, int32_t layout, float* d_bev, void* stream);
 int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
                       const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
                       int32_t layout, float* d_ddepth, float* d_dfeat, void* stream);
@@ -190,15 +194,17 @@ int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* 
  * calibration, so evaluation code can build it once per rig and reuse it.
  *   workspace: lss_plan_workspace_bytes(shape, grid) bytes, zero-filled before
  *   first use (a successful call leaves the reusable part zero again);
- *   outputs: d_cells (P), d_sorted_points (P), d_cell_range (n_cells,2),
- *   d_counts (2).  d_cell_range / d_counts are cleared by the call itself.
+ *   outputs: d_cells (P), d_sorted_points (P) and d_sorted_cells (P) (first K entries
+ *   valid, the order of the dropped points behind them is unspecified),
+ *   d_cell_range (n_cells,2), d_counts (2); all fully written by the call itself.
  * ------------------------------------------------------------------------- */
 size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid);
 int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
                    const float* d_trans, const float* d_intrins, const float* d_post_rots,
                    const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
-                   int32_t* d_cells, int32_t* d_sorted_points, int32_t* d_cell_range,
-                   int32_t* d_counts, void* d_workspace, size_t workspace_bytes, void* stream);
+                   int32_t* d_cells, int32_t* d_sorted_points, int32_t* d_sorted_cells,
+                   int32_t* d_cell_range, int32_t* d_counts, void* d_workspace,
+                   size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

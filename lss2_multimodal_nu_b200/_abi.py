@@ -49,14 +49,14 @@ SIGNATURES = {
     "lss_geometry_rank": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _G, _S, _p, _p, _p, _p, _p, _p]),
     "lss_sort_workspace_bytes": (_sz, [_i64, _i32]),
     "lss_sort_ranks": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
-    "lss_intervals": (C.c_int, [_p, _i64, _G, _i32, _p, _p, _p, _p]),
-    "lss_pool_dense_fwd": (C.c_int, [_p, _p, _p, _G, _i32, _i32, _i32, _p, _p]),
+    "lss_intervals": (C.c_int, [_p, _i64, _G, _i32, _p, _p, _p, _p, _p]),
+    "lss_pool_dense_fwd": (C.c_int, [_p, _p, _p, _p, _p, _G, _i32, _i32, _i32, _p, _p]),
     "lss_pool_dense_bwd": (C.c_int, [_p, _p, _G, _i32, _i32, _i64, _i32, _p, _p]),
     "lss_lift_stage": (C.c_int, [_p, _p, _S, _p, _p, _p]),
-    "lss_liftsplat_fwd": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _p, _p]),
+    "lss_liftsplat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _G, _S, _i32, _p, _p]),
     "lss_liftsplat_bwd": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _p, _p, _p]),
     "lss_plan_workspace_bytes": (_sz, [_S, _G]),
-    "lss_build_plan": (C.c_int, [_p] * 8 + [_G, _S, _p, _p, _p, _p, _p, _sz, _p]),
+    "lss_build_plan": (C.c_int, [_p] * 8 + [_G, _S, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lock = threading.Lock()

@@ -3,6 +3,7 @@
 #include "lss_geometry.cuh"
 #include "lss_pool.cuh"
 #include "lss_sort.cuh"
+#include "lss_sort_small.cuh"
 
 namespace lss {
 char* cuda_error_buffer() {
@@ -43,12 +44,13 @@ static int launch_geometry(const GeomArgs& ga, const GridDev& g, const LssShape*
 }
 
 static int launch_intervals(const int32_t* sorted_ranks, long long P, const GridDev& g,
-                            uint8_t* last_mask, int32_t* cell_range, int32_t* counts,
+                            uint8_t* last_mask, int32_t* sorted_cells, int32_t* cell_range, int32_t* counts,
                             uint32_t* wipe, long long wipe_words, cudaStream_t st) {
   IntervalArgs a;
   a.sorted_ranks = sorted_ranks; a.P = P; a.g = g;
   a.div_b = FastDiv(g.B); a.div_z = FastDiv(g.nx[2]); a.div_y = FastDiv(g.nx[1]);
-  a.last_mask = last_mask; a.cell_range = reinterpret_cast<int2*>(cell_range); a.counts = counts;
+  a.last_mask = last_mask; a.sorted_cells = sorted_cells;
+  a.cell_range = reinterpret_cast<int2*>(cell_range); a.counts = counts;
   a.wipe = wipe; a.wipe_words = wipe_words;
   long long blocks = (P + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
@@ -58,18 +60,27 @@ static int launch_intervals(const int32_t* sorted_ranks, long long P, const Grid
   LSS_LAUNCH_CHECK("intervals_kernel");
   return LSS_OK;
 }
-template <int kLanes, int kChunks>
+template <int kLanes>
 static int launch_bwd(const PoolBwdArgs& a, int blocks, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) {
-    LSS_CUDA_TRY(cudaFuncSetAttribute(liftsplat_bwd_nhwc_kernel<kLanes, kChunks>,
+    LSS_CUDA_TRY(cudaFuncSetAttribute(liftsplat_bwd_nhwc_kernel<kLanes>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "cudaFuncSetAttribute(bwd smem)");
   }
-  liftsplat_bwd_nhwc_kernel<kLanes, kChunks><<<blocks, 256, smem, st>>>(a);
+  liftsplat_bwd_nhwc_kernel<kLanes><<<blocks, 256, smem, st>>>(a);
   LSS_LAUNCH_CHECK("liftsplat_bwd_nhwc_kernel");
   return LSS_OK;
 }
-
+template <bool kFused>
+static int launch_pool_fwd(const PoolFwdArgs& a, int blocks, cudaStream_t st) {
+  const int G = a.G;
+  if (G <= 4) pool_fwd_nhwc_kernel<kFused, 4><<<blocks, kPoolThreads, 0, st>>>(a);
+  else if (G <= 8) pool_fwd_nhwc_kernel<kFused, 8><<<blocks, kPoolThreads, 0, st>>>(a);
+  else if (G <= 16) pool_fwd_nhwc_kernel<kFused, 16><<<blocks, kPoolThreads, 0, st>>>(a);
+  else pool_fwd_nhwc_kernel<kFused, 32><<<blocks, kPoolThreads, 0, st>>>(a);
+  LSS_LAUNCH_CHECK("pool_fwd_nhwc_kernel");
+  return LSS_OK;
+}
 }  // namespace lss
 
 using namespace lss;
@@ -161,6 +172,10 @@ int lss_sort_ranks(const int32_t* d_ranks, int64_t P, int32_t n_cells, int32_t* 
   LSS_REQUIRE(workspace_bytes >= s.total_bytes, LSS_ERR_WORKSPACE_TOO_SMALL);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(d_workspace);
+  if (s.small) {
+    LSS_CUDA_TRY(cudaMemsetAsync(w + s.off_flags, 0, s.total_bytes - s.off_flags, st), "memset sort flags");
+    return run_sort_passes_small(s, d_ranks, d_sorted_ranks, d_sorted_points, P, d_workspace, nullptr, st);
+  }
   LSS_CUDA_TRY(cudaMemsetAsync(w + s.off_control, 0, s.control_bytes, st), "memset sort control");
   SortDigits sd = sort_digits(s, d_workspace);
   long long blocks = (P + 256 * 8 - 1) / (256 * 8);
@@ -172,55 +187,56 @@ int lss_sort_ranks(const int32_t* d_ranks, int64_t P, int32_t n_cells, int32_t* 
 }
 
 int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid, int32_t B,
-                  uint8_t* d_last_mask, int32_t* d_cell_range, int32_t* d_counts, void* stream) {
+                  uint8_t* d_last_mask, int32_t* d_sorted_cells, int32_t* d_cell_range,
+                  int32_t* d_counts, void* stream) {
   LSS_REQUIRE(d_sorted_ranks && d_cell_range, LSS_ERR_NULL_POINTER);
   LSS_REQUIRE(P > 0 && P < (1ll << 30), LSS_ERR_BAD_DIMENSION);
   GridDev g;
   int rc = make_grid(grid, B, &g);
   if (rc) return rc;
-  return launch_intervals(d_sorted_ranks, P, g, d_last_mask, d_cell_range, d_counts, nullptr, 0,
-                          as_stream(stream));
+  return launch_intervals(d_sorted_ranks, P, g, d_last_mask, d_sorted_cells, d_cell_range, d_counts,
+                          nullptr, 0, as_stream(stream));
 }
 
 static int pool_fwd_common(bool fused, const float* d_depth_t, const float* d_feat_t,
                            const float* d_x, const int32_t* d_sorted_points,
-                           const int32_t* d_cell_range, const LssGrid* grid, int32_t B, int32_t C,
+                           const int32_t* d_sorted_cells, const int32_t* d_cell_range,
+                           const int32_t* d_counts, const LssGrid* grid, int32_t B, int32_t C,
                            int32_t D, int32_t HW, long long dhw, int32_t layout, float* d_bev,
                            cudaStream_t st) {
-  LSS_REQUIRE(d_sorted_points && d_cell_range && d_bev, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(d_sorted_points && d_sorted_cells && d_cell_range && d_counts && d_bev, LSS_ERR_NULL_POINTER);
   GridDev g;
   int rc = make_grid(grid, B, &g);
   if (rc) return rc;
   LSS_REQUIRE(C > 0 && C % 4 == 0, LSS_ERR_MISALIGNED);
+  LSS_REQUIRE(C <= 128, LSS_ERR_UNSUPPORTED);
   LSS_REQUIRE(aligned16(d_bev), LSS_ERR_MISALIGNED);
   LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
   PoolFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.depth_t = d_depth_t; a.feat_t = reinterpret_cast<const float4*>(d_feat_t);
   a.x = reinterpret_cast<const float4*>(d_x);
-  a.sorted_points = d_sorted_points; a.cell_range = reinterpret_cast<const int2*>(d_cell_range);
+  a.sorted_points = d_sorted_points; a.sorted_cells = d_sorted_cells; a.counts = d_counts;
+  a.cell_range = reinterpret_cast<const int2*>(d_cell_range);
   a.bev = reinterpret_cast<float4*>(d_bev);
+  a.n_cells = (uint32_t)g.n_cells;
   a.G = C / 4; a.D = D; a.HW = HW;
-  a.n_elems = (long long)g.n_cells * a.G;
-  LSS_REQUIRE(a.n_elems < (1ll << 31), LSS_ERR_BAD_DIMENSION);
+  LSS_REQUIRE((long long)g.n_cells * a.G < (1ll << 31), LSS_ERR_BAD_DIMENSION);
+  a.fill_warps = 3;
   a.div_g = FastDiv(a.G);
   a.div_dhw = FastDiv((uint32_t)(dhw > 0 ? dhw : 1)); a.div_hw = FastDiv((uint32_t)(HW > 0 ? HW : 1));
-  long long blocks = (a.n_elems + 255) / 256;
-  const long long cap = (long long)sm_count() * 8 * 4;
-  if (blocks > cap) blocks = cap;
-  if (fused) pool_fwd_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a);
-  else pool_fwd_nhwc_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a);
-  LSS_LAUNCH_CHECK("pool_fwd_nhwc_kernel");
-  return LSS_OK;
+  const int blocks = sm_count() * 6;
+  return fused ? launch_pool_fwd<true>(a, blocks, st) : launch_pool_fwd<false>(a, blocks, st);
 }
 
 int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points,
-                       const int32_t* d_cell_range, const LssGrid* grid, int32_t B, int32_t C,
+                       const int32_t* d_sorted_cells, const int32_t* d_cell_range,
+                       const int32_t* d_counts, const LssGrid* grid, int32_t B, int32_t C,
                        int32_t layout, float* d_bev, void* stream) {
   LSS_REQUIRE(d_x, LSS_ERR_NULL_POINTER);
   LSS_REQUIRE(aligned16(d_x), LSS_ERR_MISALIGNED);
-  return pool_fwd_common(false, nullptr, nullptr, d_x, d_sorted_points, d_cell_range, grid, B, C, 1, 1,
-                         1, layout, d_bev, as_stream(stream));
+  return pool_fwd_common(false, nullptr, nullptr, d_x, d_sorted_points, d_sorted_cells, d_cell_range,
+                         d_counts, grid, B, C, 1, 1, 1, layout, d_bev, as_stream(stream));
 }
 
 int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGrid* grid,
@@ -261,17 +277,17 @@ int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* sh
 }
 
 int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t,
-                      const int32_t* d_sorted_points, const int32_t* d_cell_range,
-                      const LssGrid* grid, const LssShape* shape, int32_t layout, float* d_bev,
-                      void* stream) {
+                      const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
+                      const int32_t* d_cell_range, const int32_t* d_counts, const LssGrid* grid,
+                      const LssShape* shape, int32_t layout, float* d_bev, void* stream) {
   LSS_REQUIRE(d_depth_t && d_feat_t, LSS_ERR_NULL_POINTER);
   int rc = check_shape(shape);
   if (rc) return rc;
   LSS_REQUIRE(aligned16(d_feat_t), LSS_ERR_MISALIGNED);
   const int HW = shape->fH * shape->fW;
-  return pool_fwd_common(true, d_depth_t, d_feat_t, nullptr, d_sorted_points, d_cell_range, grid,
-                         shape->B, shape->C, shape->D, HW, (long long)shape->D * HW, layout, d_bev,
-                         as_stream(stream));
+  return pool_fwd_common(true, d_depth_t, d_feat_t, nullptr, d_sorted_points, d_sorted_cells,
+                         d_cell_range, d_counts, grid, shape->B, shape->C, shape->D, HW,
+                         (long long)shape->D * HW, layout, d_bev, as_stream(stream));
 }
 
 int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
@@ -295,12 +311,10 @@ int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* 
   const int blocks = shape->B * shape->N * shape->fH;
   cudaStream_t st = as_stream(stream);
   const int G = a.G;
-  if (G <= 4) return launch_bwd<4, 1>(a, blocks, smem, st);
-  if (G <= 8) return launch_bwd<8, 1>(a, blocks, smem, st);
-  if (G <= 16) return launch_bwd<16, 1>(a, blocks, smem, st);
-  if (G <= 32) return launch_bwd<32, 1>(a, blocks, smem, st);
-  if (G <= 64) return launch_bwd<32, 2>(a, blocks, smem, st);
-  if (G <= 128) return launch_bwd<32, 4>(a, blocks, smem, st);
+  if (G <= 4) return launch_bwd<4>(a, blocks, smem, st);
+  if (G <= 8) return launch_bwd<8>(a, blocks, smem, st);
+  if (G <= 16) return launch_bwd<16>(a, blocks, smem, st);
+  if (G <= 32) return launch_bwd<32>(a, blocks, smem, st);
   return LSS_ERR_UNSUPPORTED;
 }
 
@@ -310,16 +324,17 @@ size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid) {
   if (make_grid(grid, shape->B, &g) != LSS_OK) return 0;
   const long long P = shape_points(shape);
   const SortPlan s = make_sort_plan(P, g.n_cells);
-  return s.total_bytes + 2 * align_up((size_t)P * 4, 256);
+  return make_msd_plan(s).total_bytes + 2 * align_up((size_t)P * 4, 256);
 }
 
 int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
                    const float* d_trans, const float* d_intrins, const float* d_post_rots,
                    const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
-                   int32_t* d_cells, int32_t* d_sorted_points, int32_t* d_cell_range,
-                   int32_t* d_counts, void* d_workspace, size_t workspace_bytes, void* stream) {
+                   int32_t* d_cells, int32_t* d_sorted_points, int32_t* d_sorted_cells,
+                   int32_t* d_cell_range, int32_t* d_counts, void* d_workspace,
+                   size_t workspace_bytes, void* stream) {
   LSS_REQUIRE(d_us && d_vs && d_ds && d_rots && d_trans && d_intrins && d_post_rots &&
-                  d_post_trans && d_cells && d_sorted_points && d_cell_range && d_counts &&
+                  d_post_trans && d_cells && d_sorted_points && d_sorted_cells && d_cell_range && d_counts &&
                   d_workspace, LSS_ERR_NULL_POINTER);
   int rc = check_shape(shape);
   if (rc) return rc;
@@ -329,15 +344,13 @@ int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, cons
   LSS_REQUIRE(aligned16(d_workspace), LSS_ERR_MISALIGNED);
   const long long P = shape_points(shape);
   const SortPlan s = make_sort_plan(P, g.n_cells);
-  const size_t need = s.total_bytes + 2 * align_up((size_t)P * 4, 256);
+  const size_t ws_sort = make_msd_plan(s).total_bytes;
+  const size_t need = ws_sort + 2 * align_up((size_t)P * 4, 256);
   LSS_REQUIRE(workspace_bytes >= need, LSS_ERR_WORKSPACE_TOO_SMALL);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(d_workspace);
-  int32_t* ranks = reinterpret_cast<int32_t*>(w + s.total_bytes);
-  int32_t* sorted_ranks = reinterpret_cast<int32_t*>(w + s.total_bytes + align_up((size_t)P * 4, 256));
-
-  LSS_CUDA_TRY(cudaMemsetAsync(d_cell_range, 0, (size_t)g.n_cells * 8, st), "memset cell_range");
-  LSS_CUDA_TRY(cudaMemsetAsync(d_counts, 0, 8, st), "memset counts");
+  int32_t* ranks = reinterpret_cast<int32_t*>(w + ws_sort);
+  int32_t* sorted_ranks = reinterpret_cast<int32_t*>(w + ws_sort + align_up((size_t)P * 4, 256));
 
   GeomArgs ga;
   memset(&ga, 0, sizeof(ga));
@@ -345,14 +358,31 @@ int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, cons
   ga.post_trans = d_post_trans; ga.trans = d_trans;
   ga.rots = d_rots; ga.intrins = d_intrins; ga.post_rots = d_post_rots;
   ga.raw = 1; ga.N = shape->N; ga.D = shape->D; ga.fH = shape->fH; ga.fW = shape->fW;
+  const int ppc = shape->D * shape->fH * shape->fW;
+  const MsdPlan msd = make_msd_plan(s);
+  if (msd.ok && (kSortTile - 1) / ppc + 2 <= kSmallMaxCams) {
+    // single wave: P1 = K0 + K1' + MSD partition, P2 = local sort + intervals (K2 + K3)
+    SmallGeom sg;
+    sg.enabled = true; sg.geom = ga; sg.grid = g; sg.cells = d_cells;
+    return run_msd_plan(s, msd, sg, d_sorted_points, d_sorted_cells, d_cell_range, d_counts, P, d_workspace, st);
+  }
+  LSS_CUDA_TRY(cudaMemsetAsync(d_cell_range, 0, (size_t)g.n_cells * 8, st), "memset cell_range");
+  LSS_CUDA_TRY(cudaMemsetAsync(d_counts, 0, 8, st), "memset counts");
   PointOut out{nullptr, nullptr, ranks, d_cells};
+  if (s.small) {
+    rc = launch_geometry(ga, g, shape, out, nullptr, st);
+    if (rc) return rc;
+    rc = run_sort_passes_small(s, ranks, sorted_ranks, d_sorted_points, P, d_workspace, nullptr, st);
+    if (rc) return rc;
+    return launch_intervals(sorted_ranks, P, g, nullptr, d_sorted_cells, d_cell_range, d_counts, nullptr, 0, st);
+  }
   SortDigits sd = sort_digits(s, d_workspace);
   rc = launch_geometry(ga, g, shape, out, &sd, st);
   if (rc) return rc;
   rc = run_sort_passes(s, ranks, sorted_ranks, d_sorted_points, P, d_workspace, st);
   if (rc) return rc;
   // K3 also wipes the sort's control words so the workspace is ready for the next call
-  return launch_intervals(sorted_ranks, P, g, nullptr, d_cell_range, d_counts,
+  return launch_intervals(sorted_ranks, P, g, nullptr, d_sorted_cells, d_cell_range, d_counts,
                           reinterpret_cast<uint32_t*>(w + s.off_control),
                           (long long)(s.control_bytes / 4), st);
 }

@@ -148,9 +148,9 @@ struct SortDigits {
   int stride;  // nbins_max
 };
 
-__device__ __forceinline__ int32_t quantize_point(float gx, float gy, float gz, int b,
-                                                  const GridDev& g, long long p,
-                                                  const PointOut& out) {
+__device__ __forceinline__ int32_t quantize_point_core(float gx, float gy, float gz, int b,
+                                                       const GridDev& g, long long p,
+                                                       const PointOut& out) {
   // ((geom - (bx - dx/2)) / dx).long()   reference src/model_baseline.py:92
   const float qx = __fdiv_rn(__fsub_rn(gx, g.off[0]), g.dx[0]);
   const float qy = __fdiv_rn(__fsub_rn(gy, g.off[1]), g.dx[1]);
@@ -172,9 +172,15 @@ __device__ __forceinline__ int32_t quantize_point(float gx, float gy, float gz, 
     rank = ((ix * g.nx[1] + iy) * g.nx[2] + iz) * g.B + b;
     cell = ((b * g.nx[0] + ix) * g.nx[1] + iy) * g.nx[2] + iz;
   }
-  out.ranks[p] = rank;
+  if (out.ranks) out.ranks[p] = rank;
   if (out.cells) out.cells[p] = cell;
   return rank;
+}
+
+__device__ __forceinline__ int32_t quantize_point(float gx, float gy, float gz, int b,
+                                                  const GridDev& g, long long p,
+                                                  const PointOut& out) {
+  return quantize_point_core(gx, gy, gz, b, g, p, out);
 }
 
 constexpr int kGeomThreads = 256;

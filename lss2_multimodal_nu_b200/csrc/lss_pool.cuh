@@ -18,6 +18,7 @@ struct IntervalArgs {
   GridDev g;
   FastDiv div_b, div_z, div_y;
   uint8_t* last_mask;   // or null
+  int32_t* sorted_cells;  // or null: output cell of every kept sorted point
   int2* cell_range;     // (n_cells) zero on entry
   int32_t* counts;      // {K, V} zero on entry, or null
   // control words of the sort to wipe for the next call (fused plan path)
@@ -43,7 +44,7 @@ intervals_kernel(IntervalArgs a) {
       const int32_t next = (i + 1 < a.P) ? a.sorted_ranks[i + 1] : a.g.n_cells;
       const bool head = r != prev;
       tail = r != next;
-      if (head || tail) {
+      if (head || tail || a.sorted_cells) {
         // rank = ((x*Y + y)*Z + z)*B + b  ->  output cell ((b*X + x)*Y + y)*Z + z
         uint32_t t0, b, t1, z, x, y;
         a.div_b.divmod(static_cast<uint32_t>(r), t0, b);
@@ -53,6 +54,7 @@ intervals_kernel(IntervalArgs a) {
                               static_cast<int32_t>(y)) * a.g.nx[2] + static_cast<int32_t>(z);
         if (head) a.cell_range[cell].x = static_cast<int>(i);
         if (tail) a.cell_range[cell].y = static_cast<int>(i + 1);
+        if (a.sorted_cells) a.sorted_cells[i] = cell;
       }
       ++kept;
       tails += tail ? 1 : 0;
@@ -107,68 +109,153 @@ lift_stage_kernel(const float* __restrict__ depth, const float* __restrict__ fea
 // --------------------------------------------------------------------------
 // K4 / K4a forward, channels-innermost BEV.
 //
-// The output is addressed as a flat array of float4: element e belongs to
-// output cell e / G (G = C/4 vectors per cell) and holds channels 4*(e % G)..+3.
-// Cells are numbered ((b*X + x)*Y + y)*Z + z, so consecutive elements are
-// consecutive in memory: every warp store is one contiguous 512-byte line, and
-// every output element -- empty voxels included -- is written exactly once
-// (this replaces torch.zeros + index_put + cat of src/model_baseline.py:120-124).
-// Each lane walks its cell's run of sorted points in ascending order, so the
-// per-voxel sum order is fixed: results are bit-reproducible run to run.
-//   kFused:  acc += depth_t[pixel*D + d] * feat_t[pixel, 4*chunk..]   (K4)
-//   !kFused: acc += x[point, 4*chunk..]                                (K4a)
+// The BEV map is addressed as (cell, G) float4 vectors, cell = ((b*X + x)*Y + y)*Z + z
+// and G = C/4, so one voxel is one contiguous line.  Every output element is
+// written exactly once (this replaces torch.zeros + index_put + cat of
+// reference src/model_baseline.py:120-124) by two kinds of warps that run side
+// by side in every CTA:
+//   * FILL warps stream zeros into the empty voxels (about 75 % of the map at
+//     the headline config), one contiguous 512-byte line per warp store;
+//   * REDUCE warps do the warp-level segmented reduction over the sorted point
+//     list: kLanes lanes (a power of two >= G) own one voxel interval at a time,
+//     each lane one float4 of channels.  A group loads kLanes consecutive sorted
+//     points cooperatively (point id, output cell, depth), broadcasts them with
+//     shuffles and walks them in order: a change of cell closes the running sum
+//     (one 16*G-byte store) and opens the next.  A group owns the intervals that
+//     START inside its chunk and follows the last one past the chunk end.
+// The walk order is the sort order, so per-voxel sums are bit-reproducible.
+//   kFused:  acc += depth_t[pixel*D + d] * feat_t[pixel, :]   (K4: the frustum
+//            tensor of src/modules.py:84 is never formed)
+//   !kFused: acc += x[point, :]                                (K4a)
 // --------------------------------------------------------------------------
 struct PoolFwdArgs {
-  const float* depth_t;        // (BN*HW, D)        fused
-  const float4* feat_t;        // (BN*HW, G)        fused
-  const float4* x;             // (P, G)            dense
-  const int32_t* sorted_points;
-  const int2* cell_range;
+  const float* depth_t;           // (BN*HW, D)        fused
+  const float4* feat_t;           // (BN*HW, G)        fused
+  const float4* x;                // (P, G)            dense
+  const int32_t* sorted_points;   // (P) first K valid
+  const int32_t* sorted_cells;    // (P) output cell of each sorted point, first K valid
+  const int32_t* counts;          // {K, V}
+  const int2* cell_range;         // (n_cells) start >= end: empty
   float4* bev;
-  long long n_elems;           // n_cells * G
+  uint32_t n_cells;
   int G, D, HW;
+  int fill_warps;                 // warps per CTA that zero-fill (the rest reduce)
   FastDiv div_g, div_dhw, div_hw;
 };
 
-template <bool kFused>
-__global__ void __launch_bounds__(256)
+constexpr int kPoolThreads = 256;
+constexpr int kPoolWarps = kPoolThreads / 32;
+
+template <bool kFused, int kLanes>
+__global__ void __launch_bounds__(kPoolThreads)
 pool_fwd_nhwc_kernel(PoolFwdArgs a) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.n_elems; e += stride) {
-    uint32_t cell, chunk;
-    a.div_g.divmod(static_cast<uint32_t>(e), cell, chunk);
-    const int2 range = __ldg(a.cell_range + cell);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = range.x; i < range.y; i += 4) {
-      const int n = min(4, range.y - i);
-      int32_t pt[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) pt[k] = (k < n) ? __ldg(a.sorted_points + i + k) : 0;
-      float dv[4];
-      float4 f[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (kFused) {
-          uint32_t bn, rem, d, hw;
-          a.div_dhw.divmod(static_cast<uint32_t>(pt[k]), bn, rem);
-          a.div_hw.divmod(rem, d, hw);
-          const uint32_t pix = bn * a.HW + hw;
-          dv[k] = (k < n) ? __ldg(a.depth_t + (size_t)pix * a.D + d) : 0.f;
-          f[k] = (k < n) ? ldg_f4(a.feat_t + (size_t)pix * a.G + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          dv[k] = (k < n) ? 1.f : 0.f;
-          f[k] = (k < n) ? ldg_f4(a.x + (size_t)pt[k] * a.G + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int kGroups = 32 / kLanes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if (warp < a.fill_warps) {
+    // ---- FILL: zeros into empty voxels ------------------------------------
+    // One coalesced load fetches the intervals of 32 consecutive cells (the next block
+    // of 32 is prefetched before the stores go out); the emptiness bits are shared
+    // with a ballot and the cells' 32*G float4 are covered by G full-warp stores.
+    const uint32_t n_fill = gridDim.x * static_cast<uint32_t>(a.fill_warps);
+    uint32_t c0 = (blockIdx.x * a.fill_warps + warp) * 32u;
+    int2 r = (c0 + lane < a.n_cells) ? __ldg(a.cell_range + c0 + lane) : make_int2(0, 1);
+    while (c0 < a.n_cells) {
+      const uint32_t c1 = c0 + n_fill * 32u;
+      const int2 rn = (c1 + lane < a.n_cells) ? __ldg(a.cell_range + c1 + lane) : make_int2(0, 1);
+      const uint32_t empty = __ballot_sync(0xffffffffu, r.x >= r.y);
+      if (empty) {
+        float4* dst = a.bev + (size_t)c0 * a.G;
+        for (int k = 0; k < a.G; ++k) {
+          const uint32_t e = k * 32u + lane;
+          const uint32_t cl = a.div_g.div(e);
+          if ((empty >> cl) & 1u) st_stream_f4(dst + e, zero4);
         }
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc.x = fmaf(dv[k], f[k].x, acc.x);
-        acc.y = fmaf(dv[k], f[k].y, acc.y);
-        acc.z = fmaf(dv[k], f[k].z, acc.z);
-        acc.w = fmaf(dv[k], f[k].w, acc.w);
-      }
+      r = rn;
+      c0 = c1;
     }
-    st_stream_f4(a.bev + e, acc);
+    return;
+  }
+
+  // ---- REDUCE: segmented sums over the sorted points --------------------------
+  const int rw = warp - a.fill_warps, n_rw = kPoolWarps - a.fill_warps;
+  const int grp = lane / kLanes, sub = lane % kLanes;
+  const uint32_t gmask = (kLanes == 32) ? 0xffffffffu : (((1u << kLanes) - 1u) << (grp * kLanes));
+  const int K = __ldg(a.counts);
+  const int n_chunks = (K + kLanes - 1) / kLanes;
+  const int slot = (blockIdx.x * n_rw + rw) * kGroups + grp;
+  const int n_slots = gridDim.x * n_rw * kGroups;
+  const bool lane_active = sub < a.G;  // kLanes may exceed G (e.g. C = 80: 20 of 32 lanes)
+
+  for (int chunk = slot; chunk < n_chunks; chunk += n_slots) {
+    int base = chunk * kLanes;
+    int cur_cell = -1;
+    float4 acc = zero4;
+    bool first = true;
+    while (true) {
+      // cooperative load of kLanes consecutive sorted points
+      const int i = base + sub;
+      const bool valid = i < K;
+      const int32_t pt = valid ? __ldg(a.sorted_points + i) : 0;
+      const int32_t cell = valid ? __ldg(a.sorted_cells + i) : -1;
+      int32_t prev = __shfl_up_sync(gmask, cell, 1, kLanes);
+      if (sub == 0) prev = (valid && i > 0) ? __ldg(a.sorted_cells + i - 1) : -1;
+      const bool head = valid && (cell != prev);
+      uint32_t row;   // feature row (pixel, or point for the dense variant)
+      float dv = 0.f;
+      if (kFused) {
+        uint32_t bn, rem, d, hw;
+        a.div_dhw.divmod(static_cast<uint32_t>(pt), bn, rem);
+        a.div_hw.divmod(rem, d, hw);
+        row = bn * a.HW + hw;
+        if (valid) dv = __ldg(a.depth_t + (size_t)row * a.D + d);
+      } else {
+        row = static_cast<uint32_t>(pt);
+        dv = 1.f;
+      }
+      bool done = false;
+#pragma unroll
+      for (int j0 = 0; j0 < kLanes; j0 += 4) {
+        if (done) break;
+        int32_t cj[4];
+        bool hj[4];
+        float dj[4];
+        float4 fj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          cj[u] = __shfl_sync(gmask, cell, j, kLanes);
+          hj[u] = __shfl_sync(gmask, head ? 1 : 0, j, kLanes) != 0;
+          dj[u] = __shfl_sync(gmask, dv, j, kLanes);
+          const uint32_t rj = __shfl_sync(gmask, row, j, kLanes);
+          const float4* src = kFused ? a.feat_t : a.x;
+          fj[u] = (cj[u] >= 0 && lane_active) ? ldg_f4(src + (size_t)rj * a.G + sub) : zero4;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (done) break;
+          if (cj[u] < 0) { done = true; break; }            // ran off the end of the kept points
+          if (hj[u]) {
+            if (!first) { done = true; break; }              // next group's interval starts here
+            if (cur_cell >= 0 && lane_active) st_stream_f4(a.bev + (size_t)cur_cell * a.G + sub, acc);
+            acc = zero4;
+            cur_cell = cj[u];
+          }
+          if (cur_cell >= 0) {
+            acc.x = fmaf(dj[u], fj[u].x, acc.x);
+            acc.y = fmaf(dj[u], fj[u].y, acc.y);
+            acc.z = fmaf(dj[u], fj[u].z, acc.z);
+            acc.w = fmaf(dj[u], fj[u].w, acc.w);
+          }
+        }
+      }
+      if (done || cur_cell < 0) break;   // closed by a foreign head / end, or no interval started here
+      first = false;                     // keep following the open interval into the next chunk
+      base += kLanes;
+    }
+    if (cur_cell >= 0 && lane_active) st_stream_f4(a.bev + (size_t)cur_cell * a.G + sub, acc);
   }
 }
 
@@ -195,12 +282,17 @@ pool_dense_bwd_nhwc_kernel(const float4* __restrict__ dbev, const int32_t* __res
 // One CTA per feature-map row (bn, h): its fW pixels x D depth bins.  A warp
 // owns one pixel at a time and keeps that pixel's context vector in registers;
 // kLanes lanes (a power of two >= C/4) cooperate on one point, 32/kLanes points
-// are in flight per step.  For every kept point the voxel gradient g (C floats,
-// one contiguous line of the channels-innermost dBEV) is gathered once and used
-// twice:   d_depth[d] = <g, feat>   (shuffle reduction over the point's lanes)
-//          d_feat    += depth[d] * g (register accumulation over d)
-// Only OCCUPIED voxels of dBEV are ever read.  Results are staged in shared
-// memory and written as whole (d, :) / (c, :) rows.  No atomics: deterministic.
+// sit side by side in the warp and kUnroll such steps are issued back to back,
+// so up to kUnroll*32/kLanes voxel-gradient lines are in flight per warp.
+// For every kept point the voxel gradient g (C floats, one contiguous line of
+// the channels-innermost dBEV) is gathered once and used twice:
+//     d_depth[d] = <g, feat>      d_feat += depth[d] * g
+// Only OCCUPIED voxels of dBEV are ever read.  <g, feat> has C terms of order
+// one that cancel, so it is accumulated in float64 (B200 has the FP64 pipe) and
+// the kUnroll partial dots of a lane are reduced together with a transposed
+// butterfly (2*kUnroll shuffles instead of kUnroll*log2(kLanes)).  Results are
+// staged in shared memory and written as whole (d, :) / (c, :) rows.  No
+// atomics anywhere: bit-reproducible.
 // --------------------------------------------------------------------------
 struct PoolBwdArgs {
   const float4* dbev;       // (n_cells, G)
@@ -212,12 +304,14 @@ struct PoolBwdArgs {
   int D, fH, fW, C, G;
 };
 
-template <int kLanes, int kChunks>
-__global__ void __launch_bounds__(256)
+template <int kLanes>
+__global__ void __launch_bounds__(512)
 liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
   extern __shared__ float s_mem[];
-  constexpr int kPts = 32 / kLanes;  // points per warp step
-  constexpr int kUnroll = 4;
+  constexpr int kPts = 32 / kLanes;                 // points per warp step
+  constexpr int kUnroll = kLanes >= 8 ? 8 : kLanes; // steps in flight
+  constexpr int kLog = kLanes == 32 ? 5 : kLanes == 16 ? 4 : kLanes == 8 ? 3 : 2;
+  constexpr int kLogU = kUnroll == 8 ? 3 : 2;
   const int bn = blockIdx.x / a.fH, h = blockIdx.x % a.fH;
   const int HW = a.fH * a.fW;
   int32_t* s_cells = reinterpret_cast<int32_t*>(s_mem);  // [D][fW]
@@ -226,74 +320,80 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
   const int dfs = a.fW + 1;
   for (int i = threadIdx.x; i < a.D * a.fW; i += blockDim.x) {
     const int d = i / a.fW, w = i - d * a.fW;
-    s_cells[i] = a.cells[((size_t)(bn * a.D + d) * a.fH + h) * a.fW + w];
+    s_cells[i] = __ldg(a.cells + ((size_t)(bn * a.D + d) * a.fH + h) * a.fW + w);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int grp = lane / kLanes, sub = lane % kLanes;
+  const bool lane_active = sub < a.G;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // which of the kUnroll dots this lane ends up holding after the transposed butterfly
+  int my_u = 0;
+#pragma unroll
+  for (int k = 0; k < kLogU; ++k)
+    if (sub & (kLanes >> (k + 1))) my_u += kUnroll >> (k + 1);
+  const bool writer = (sub & ((kLanes >> kLogU) - 1)) == 0;
+
   for (int w = warp; w < a.fW; w += nwarps) {
     const size_t pix = (size_t)bn * HW + h * a.fW + w;
-    float4 f[kChunks], acc[kChunks];
-#pragma unroll
-    for (int k = 0; k < kChunks; ++k) {
-      const int chunk = sub + k * kLanes;
-      f[k] = (chunk < a.G) ? ldg_f4(a.feat_t + pix * a.G + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
-      acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    const float4 f = lane_active ? ldg_f4(a.feat_t + pix * a.G + sub) : zero4;
+    float4 acc = zero4;
     for (int d0 = 0; d0 < a.D; d0 += kPts * kUnroll) {
-      float4 g[kUnroll][kChunks];
+      float4 g[kUnroll];
       float dv[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int d = d0 + u * kPts + grp;
         const int32_t cell = (d < a.D) ? s_cells[d * a.fW + w] : -1;
         dv[u] = (d < a.D) ? __ldg(a.depth_t + pix * a.D + d) : 0.f;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) {
-          const int chunk = sub + k * kLanes;
-          g[u][k] = (cell >= 0 && chunk < a.G) ? ldg_f4(a.dbev + (size_t)cell * a.G + chunk)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        g[u] = (cell >= 0 && lane_active) ? ldg_f4(a.dbev + (size_t)cell * a.G + sub) : zero4;
       }
+      double dot[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const int d = d0 + u * kPts + grp;
-        // <g, feat> has C terms of order one that cancel: accumulate it in float64 so the
-        // result is the correctly rounded sum (abs 1e-6 parity bar); B200 has the FP64 pipe.
-        double dot = 0.0;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) {
-          dot = fma((double)g[u][k].x, (double)f[k].x, dot);
-          dot = fma((double)g[u][k].y, (double)f[k].y, dot);
-          dot = fma((double)g[u][k].z, (double)f[k].z, dot);
-          dot = fma((double)g[u][k].w, (double)f[k].w, dot);
-          acc[k].x = fmaf(dv[u], g[u][k].x, acc[k].x);
-          acc[k].y = fmaf(dv[u], g[u][k].y, acc[k].y);
-          acc[k].z = fmaf(dv[u], g[u][k].z, acc[k].z);
-          acc[k].w = fmaf(dv[u], g[u][k].w, acc[k].w);
-        }
-#pragma unroll
-        for (int o = kLanes / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if (sub == 0 && d < a.D) s_dd[d * a.fW + w] = static_cast<float>(dot);
+        double t = static_cast<double>(g[u].x) * static_cast<double>(f.x);
+        t = fma(static_cast<double>(g[u].y), static_cast<double>(f.y), t);
+        t = fma(static_cast<double>(g[u].z), static_cast<double>(f.z), t);
+        t = fma(static_cast<double>(g[u].w), static_cast<double>(f.w), t);
+        dot[u] = t;
+        acc.x = fmaf(dv[u], g[u].x, acc.x);
+        acc.y = fmaf(dv[u], g[u].y, acc.y);
+        acc.z = fmaf(dv[u], g[u].z, acc.z);
+        acc.w = fmaf(dv[u], g[u].w, acc.w);
       }
+      // transposed butterfly: halve the number of live values at every exchange
+#pragma unroll
+      for (int k = 0; k < kLog; ++k) {
+        const int o = kLanes >> (k + 1);
+        if (k < kLogU) {
+          const int half = kUnroll >> (k + 1);
+          const bool upper = (sub & o) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const double send = upper ? dot[i] : dot[i + half];
+            const double keep = upper ? dot[i + half] : dot[i];
+            dot[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        } else {
+          dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
+        }
+      }
+      const int d = d0 + my_u * kPts + grp;
+      if (writer && d < a.D) s_dd[d * a.fW + w] = static_cast<float>(dot[0]);
     }
     // fold the kPts point-groups of the warp together
 #pragma unroll
-    for (int k = 0; k < kChunks; ++k) {
-#pragma unroll
-      for (int o = kLanes; o < 32; o <<= 1) {
-        acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
-        acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
-        acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o);
-        acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
-      }
-      const int chunk = sub + k * kLanes;
-      if (grp == 0 && chunk < a.G) {
-        s_df[(chunk * 4 + 0) * dfs + w] = acc[k].x;
-        s_df[(chunk * 4 + 1) * dfs + w] = acc[k].y;
-        s_df[(chunk * 4 + 2) * dfs + w] = acc[k].z;
-        s_df[(chunk * 4 + 3) * dfs + w] = acc[k].w;
-      }
+    for (int o = kLanes; o < 32; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (grp == 0 && lane_active) {
+      s_df[(sub * 4 + 0) * dfs + w] = acc.x;
+      s_df[(sub * 4 + 1) * dfs + w] = acc.y;
+      s_df[(sub * 4 + 2) * dfs + w] = acc.z;
+      s_df[(sub * 4 + 3) * dfs + w] = acc.w;
     }
   }
   __syncthreads();

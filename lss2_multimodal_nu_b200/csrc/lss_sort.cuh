@@ -38,12 +38,20 @@ struct SortPlan {
   int bits[4];
   int shift[4];
   long long tiles;
+  bool small;  // single-wave kernel (lss_sort_small.cuh) instead of the chained look-back
   // workspace layout (byte offsets)
   size_t off_tmp_keys, off_tmp_vals, off_control, off_hist, off_ticket, off_status[4];
+  size_t off_flags, off_ctl;  // single-wave control words
   size_t control_bytes, total_bytes;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Tiles at or below this count run the single-wave kernel (lss_sort_small.cuh),
+// which sorts at most 10 bits per pass (1024 bins keep its per-warp counters in
+// 48 KB of static shared memory).
+constexpr int kSmallMaxTilesPlan = 128;
+constexpr int kSmallMaxBitsPlan = 10;
 
 inline SortPlan make_sort_plan(long long P, int32_t n_cells) {
   SortPlan s;
@@ -52,7 +60,11 @@ inline SortPlan make_sort_plan(long long P, int32_t n_cells) {
   while ((1ll << kb) <= (long long)n_cells) ++kb;  // bit length of the sentinel rank
   if (kb < 1) kb = 1;
   s.key_bits = kb;
-  s.passes = (kb + kSortMaxBits - 1) / kSortMaxBits;
+  s.tiles = (P + kSortTile - 1) / kSortTile;
+  if (s.tiles < 1) s.tiles = 1;
+  s.small = s.tiles <= kSmallMaxTilesPlan;
+  const int max_bits = s.small ? kSmallMaxBitsPlan : kSortMaxBits;
+  s.passes = (kb + max_bits - 1) / max_bits;
   const int base = kb / s.passes, rem = kb % s.passes;
   int sh = 0;
   for (int i = 0; i < s.passes; ++i) {
@@ -60,17 +72,22 @@ inline SortPlan make_sort_plan(long long P, int32_t n_cells) {
     s.shift[i] = sh;
     sh += s.bits[i];
   }
-  s.tiles = (P + kSortTile - 1) / kSortTile;
-  if (s.tiles < 1) s.tiles = 1;
   size_t off = 0;
   s.off_tmp_keys = off; off += align_up((size_t)P * 4, 256);
   s.off_tmp_vals = off; off += align_up((size_t)P * 4, 256);
   s.off_control = off;
-  s.off_hist = off; off += (size_t)4 * kSortMaxBins * 4;
-  s.off_ticket = off; off += 256;
-  for (int i = 0; i < s.passes; ++i) {
-    s.off_status[i] = off;
-    off += align_up((size_t)s.tiles * (size_t)(1 << s.bits[i]) * 4, 256);
+  if (s.small) {
+    // rows [tiles][1024] u16 | flags [tiles] u32 | ctl
+    off += align_up((size_t)s.tiles * (1u << kSmallMaxBitsPlan) * 2, 256);
+    s.off_flags = off; off += align_up((size_t)s.tiles * 4, 256);
+    s.off_ctl = off; off += 256;
+  } else {
+    s.off_hist = off; off += (size_t)4 * kSortMaxBins * 4;
+    s.off_ticket = off; off += 256;
+    for (int i = 0; i < s.passes; ++i) {
+      s.off_status[i] = off;
+      off += align_up((size_t)s.tiles * (size_t)(1 << s.bits[i]) * 4, 256);
+    }
   }
   s.control_bytes = off - s.off_control;
   s.total_bytes = off;

@@ -181,15 +181,17 @@ def sort_ranks(ranks: torch.Tensor, n_cells: int):
 
 
 def intervals(sorted_ranks: torch.Tensor, grid: GridSpec, B: int, want_last_mask=False):
-    """Run detection -> (cell_range (n_cells,2) int32, counts (2) int32 [K, V], last_mask|None)."""
+    """Run detection -> (cell_range (n_cells,2) int32, counts (2) int32 [K, V], last_mask|None,
+    sorted_cells (P) int32)."""
     dev = _need_cuda(sorted_ranks)
     P = sorted_ranks.numel()
     cell_range = torch.zeros((grid.n_cells(B), 2), dtype=torch.int32, device=dev)
     counts = torch.zeros(2, dtype=torch.int32, device=dev)
     last = torch.empty(P, dtype=torch.uint8, device=dev) if want_last_mask else None
-    _abi.call("lss_intervals", _ptr(sorted_ranks), P, grid.c(), B, _ptr(last), _ptr(cell_range),
-              _ptr(counts), _stream(dev))
-    return cell_range, counts, last
+    sorted_cells = torch.empty(P, dtype=torch.int32, device=dev)
+    _abi.call("lss_intervals", _ptr(sorted_ranks), P, grid.c(), B, _ptr(last), _ptr(sorted_cells),
+              _ptr(cell_range), _ptr(counts), _stream(dev))
+    return cell_range, counts, last, sorted_cells
 
 
 # --------------------------------------------------------------------------
@@ -205,7 +207,8 @@ class Plan:
     fH: int
     fW: int
     cells: torch.Tensor          # (P) int32 output cell of each point, -1 if dropped
-    sorted_points: torch.Tensor  # (P) int32 point index in rank order (kept points first)
+    sorted_points: torch.Tensor  # (P) int32 point index in rank order (first K entries valid)
+    sorted_cells: torch.Tensor   # (P) int32 output cell of each sorted point (first K valid)
     cell_range: torch.Tensor     # (n_cells, 2) int32 [start, end) into sorted_points
     counts: torch.Tensor         # (2) int32 {K, V}
 
@@ -245,17 +248,19 @@ def build_plan(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: Gr
     ws = _plan_workspace(dev, st, shape, g)
     cells = torch.empty(P, dtype=torch.int32, device=dev)
     sorted_points = torch.empty(P, dtype=torch.int32, device=dev)
+    sorted_cells = torch.empty(P, dtype=torch.int32, device=dev)
     cell_range = torch.empty((grid.n_cells(B), 2), dtype=torch.int32, device=dev)
     counts = torch.empty(2, dtype=torch.int32, device=dev)
     try:
         _abi.call("lss_build_plan", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
                   _ptr(_f32c(rots)), _ptr(_f32c(trans)), _ptr(_f32c(intrins)),
                   _ptr(_f32c(post_rots)), _ptr(_f32c(post_trans)), g, shape, _ptr(cells),
-                  _ptr(sorted_points), _ptr(cell_range), _ptr(counts), _ptr(ws), ws.numel(), st)
+                  _ptr(sorted_points), _ptr(sorted_cells), _ptr(cell_range), _ptr(counts), _ptr(ws),
+                  ws.numel(), st)
     except _abi.LssError:
         ws.zero_()  # a failed call may leave the control words dirty
         raise
-    return Plan(grid, B, N, D, fH, fW, cells, sorted_points, cell_range, counts)
+    return Plan(grid, B, N, D, fH, fW, cells, sorted_points, sorted_cells, cell_range, counts)
 
 
 def plan_from_geom(geom: torch.Tensor, grid: GridSpec) -> Plan:
@@ -264,8 +269,8 @@ def plan_from_geom(geom: torch.Tensor, grid: GridSpec) -> Plan:
     B, N, D, fH, fW, _ = geom.shape
     q = quantize_rank(geom, grid, B)
     sk, sp = sort_ranks(q["ranks"], grid.n_cells(B))
-    cell_range, counts, _ = intervals(sk, grid, B)
-    return Plan(grid, B, N, D, fH, fW, q["cells"], sp, cell_range, counts)
+    cell_range, counts, _, sorted_cells = intervals(sk, grid, B)
+    return Plan(grid, B, N, D, fH, fW, q["cells"], sp, sorted_cells, cell_range, counts)
 
 
 # --------------------------------------------------------------------------
@@ -321,8 +326,8 @@ class _LiftSplat(torch.autograd.Function):
         depth_t, feat_t = lift_stage(depth, feat, plan)
         bev = _alloc_bev(plan, C, dev)
         _abi.call("lss_liftsplat_fwd", _ptr(depth_t), _ptr(feat_t), _ptr(plan.sorted_points),
-                  _ptr(plan.cell_range), plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC,
-                  _ptr(bev), _stream(dev))
+                  _ptr(plan.sorted_cells), _ptr(plan.cell_range), _ptr(plan.counts), plan.grid.c(),
+                  plan.shape(C), _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
         ctx.plan = plan
         ctx.C = C
         ctx.in_dtypes = (depth.dtype, feat.dtype)
@@ -373,8 +378,9 @@ class _PoolDense(torch.autograd.Function):
         if x2.shape[0] != plan.P:
             raise RuntimeError("x has %d points, plan has %d" % (x2.shape[0], plan.P))
         bev = _alloc_bev(plan, C, dev)
-        _abi.call("lss_pool_dense_fwd", _ptr(x2), _ptr(plan.sorted_points), _ptr(plan.cell_range),
-                  plan.grid.c(), plan.B, C, _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
+        _abi.call("lss_pool_dense_fwd", _ptr(x2), _ptr(plan.sorted_points), _ptr(plan.sorted_cells),
+                  _ptr(plan.cell_range), _ptr(plan.counts), plan.grid.c(), plan.B, C,
+                  _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
         ctx.plan = plan
         ctx.x_shape = tuple(x.shape)
         ctx.x_dtype = x.dtype

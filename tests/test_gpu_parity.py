@@ -136,7 +136,7 @@ def test_sort_and_intervals_bit_exact(golden_dir, name):
         assert (np.sort(ref_pts[s0:e0]) == cpu(sp)[s0:e0]).all()
     assert (cpu(sk)[K:] == n_cells).all()
     assert (np.sort(cpu(sp)[K:]) == np.nonzero(~g["kept"])[0]).all()
-    cell_range, counts, last = F.intervals(sk, grid, B, want_last_mask=True)
+    cell_range, counts, last, sorted_cells = F.intervals(sk, grid, B, want_last_mask=True)
     assert cpu(counts).tolist() == [K, int(g["last_mask"].sum())]
     assert (cpu(last)[:K].astype(bool) == g["last_mask"]).all() and not cpu(last)[K:].any()
     # dense table: every occupied cell's range holds exactly its rank
@@ -144,6 +144,7 @@ def test_sort_and_intervals_bit_exact(golden_dir, name):
     lens = cr[:, 1] - cr[:, 0]
     assert lens.sum() == K and (lens >= 0).all()
     cells = cpu(q["cells"])
+    assert (cpu(sorted_cells)[:K] == cells[cpu(sp)[:K]]).all()
     occ = np.nonzero(lens)[0]
     for c in occ[:: max(1, len(occ) // 200)]:
         pts = cpu(sp)[cr[c, 0]:cr[c, 1]]
@@ -161,6 +162,7 @@ def test_fused_plan_matches_stepwise(golden_dir, name):
         assert (cpu(getattr(plan, a)) == cpu(getattr(step, a))).all(), a
     K = int(cpu(plan.counts)[0])
     assert (cpu(plan.sorted_points)[:K] == cpu(step.sorted_points)[:K]).all()
+    assert (cpu(plan.sorted_cells)[:K] == cpu(step.sorted_cells)[:K]).all()
     # the workspace is reusable: a second call gives the same plan
     plan2 = F.build_plan(us, vs, ds, *(dev(g[k]) for k in CAL), grid)
     assert (cpu(plan2.sorted_points)[:K] == cpu(plan.sorted_points)[:K]).all()
@@ -290,7 +292,7 @@ def test_config2_full_size_digests(golden_dir):
     sorts = compact[cpu(plan.sorted_points)[:K]].astype(np.int32)
     assert sha(sorts) == g["sha256"]["sorts_i32"]
     sk, _ = F.sort_ranks(out["ranks"], grid.n_cells(cfg.B))
-    _, _, last = F.intervals(sk, grid, cfg.B, want_last_mask=True)
+    _, _, last, _ = F.intervals(sk, grid, cfg.B, want_last_mask=True)
     assert sha(cpu(last)[:K]) == g["sha256"]["last_mask_u8"]
     depth = dev(ft["depth"]).requires_grad_(True); feat = dev(ft["feat"]).requires_grad_(True)
     bev = F.lift_splat(depth, feat, plan)
