@@ -174,11 +174,9 @@ def run_ours(args, cfg):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from lss2_multimodal_nu_b200 import _abi, functional as F, synthetic as S
+    from lss2_multimodal_nu_b200 import _abi, functional as F, shard, synthetic as S
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = shard.env_world()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
@@ -201,7 +199,7 @@ def run_ours(args, cfg):
     BN, HW = cfg.B * cfg.N, cfg.fH * cfg.fW
     host, sets = [], []
     for s in range(args.sets):
-        seed = 1234 + 1000 * rank + s
+        seed = shard.rank_seed(1234, rank, s)
         cal = S.make_calibration(cfg, seed); ft = S.make_features(cfg, seed)
         h = {k: torch.from_numpy(v).pin_memory() for k, v in {**cal, **ft}.items()}
         host.append(h)
@@ -286,12 +284,9 @@ def run_ours(args, cfg):
         clocks.stop()
         elapsed_ms = e0.elapsed_time(e1)
         barrier()
-        if world > 1:
-            t = torch.tensor([elapsed_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            elapsed_ms = float(t.item())
+        value = shard.aggregate_throughput(cfg.B * args.steps, elapsed_ms, dev)   # all samples / slowest rank
+        elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
         ms_per_step = elapsed_ms / args.steps
-        value = world * cfg.B * args.steps / (elapsed_ms * 1e-3)
 
         # ---- per-kernel timing (CUDA events on the launching stream), cold rotating sets ----
         def time_kernel(fn, n):
@@ -366,11 +361,8 @@ def run_ours(args, cfg):
     b.record()
     torch.cuda.synchronize()
     e2e_ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e = {"value": world * cfg.B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hb,
+    e2e_value = shard.aggregate_throughput(cfg.B * e2e_steps, e2e_ms, dev)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hb,
            "d2h_bytes_per_step": db, "steps": e2e_steps,
            "note": "public API (build_plan + lift_splat autograd), pinned host depth/feat/calibration in, "
                    "d_depth/d_feat out, per-step stream sync; upstream dBEV stays on the device"}
