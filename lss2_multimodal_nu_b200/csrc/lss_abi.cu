@@ -4,6 +4,7 @@
 #include "lss_pool.cuh"
 #include "lss_sort.cuh"
 #include "lss_sort_small.cuh"
+#include "lss_partition.cuh"
 
 namespace lss {
 char* cuda_error_buffer() {
@@ -60,6 +61,87 @@ static int launch_intervals(const int32_t* sorted_ranks, long long P, const Grid
   LSS_LAUNCH_CHECK("intervals_kernel");
   return LSS_OK;
 }
+
+// ---- co-resident partition path (lss_partition.cuh) -------------------------------------
+struct CoopPlan {
+  bool ok;
+  int tiles, hi_bits, lo_bits, n_buckets;
+  size_t off_keys, off_vals, off_rows, off_excl, off_totals, off_bucket_start, off_barrier, total_bytes;
+};
+
+static int coop_capacity() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_coop_kernel, kPartThreads, 0) != cudaSuccess)
+      per_sm = 0;
+    cached[dev] = per_sm * sm_count() + 1;  // +1: 0 means "not queried"
+  }
+  return cached[dev] - 1;
+}
+
+static CoopPlan make_coop_plan(long long P, int32_t n_cells, int ppc, bool query_device) {
+  CoopPlan c;
+  memset(&c, 0, sizeof(c));
+  int kb = 0;
+  while ((1ll << kb) <= (long long)n_cells) ++kb;
+  if (kb < 2) kb = 2;
+  c.hi_bits = kb - 1 < kPartMaxBits ? kb - 1 : kPartMaxBits;
+  c.lo_bits = kb - c.hi_bits;
+  c.n_buckets = 1 << c.hi_bits;
+  const long long tiles = (P + kPartTile - 1) / kPartTile;
+  c.tiles = (int)tiles;
+  c.ok = c.lo_bits <= kLocalMaxBits && tiles <= kPartMaxTiles && ppc > 0 &&
+         (kPartTile - 1) / ppc + 2 <= kPartMaxCams;
+  if (c.ok && query_device) c.ok = tiles <= coop_capacity();
+  size_t off = 0;
+  c.off_keys = off; off += align_up((size_t)P * 4, 256);
+  c.off_vals = off; off += align_up((size_t)P * 4, 256);
+  c.off_rows = off; off += align_up((size_t)tiles * kPartMaxBins * 2, 256);
+  c.off_excl = off; off += align_up((size_t)tiles * kPartMaxBins * 4, 256);
+  c.off_totals = off; off += align_up((size_t)kPartMaxBins * 4, 256);
+  c.off_bucket_start = off; off += align_up((size_t)(kPartMaxBins + 1) * 4, 256);
+  c.off_barrier = off; off += 256;
+  c.total_bytes = off;
+  return c;
+}
+
+static int run_coop_plan(const CoopPlan& c, const GeomArgs& ga, const GridDev& g, long long P,
+                         int32_t* d_cells, int32_t* sorted_points, int32_t* sorted_cells,
+                         int32_t* cell_range, int32_t* counts, void* ws, cudaStream_t st) {
+  char* w = static_cast<char*>(ws);
+  PartitionArgs a;
+  memset(&a, 0, sizeof(a));
+  a.geom = ga; a.grid = g;
+  const int hw = ga.fH * ga.fW;
+  a.div_ppc = FastDiv((uint32_t)(ga.D * hw)); a.div_hw = FastDiv((uint32_t)hw);
+  a.div_w = FastDiv((uint32_t)ga.fW); a.div_n = FastDiv((uint32_t)ga.N);
+  a.P = P; a.tiles = c.tiles; a.shift = c.lo_bits; a.bits = c.hi_bits;
+  a.cells = d_cells;
+  a.part_keys = reinterpret_cast<int32_t*>(w + c.off_keys);
+  a.part_vals = reinterpret_cast<int32_t*>(w + c.off_vals);
+  a.rows = reinterpret_cast<uint16_t*>(w + c.off_rows);
+  a.excl = reinterpret_cast<uint32_t*>(w + c.off_excl);
+  a.totals = reinterpret_cast<uint32_t*>(w + c.off_totals);
+  a.bucket_start = reinterpret_cast<uint32_t*>(w + c.off_bucket_start);
+  a.counts = counts;
+  a.barrier = reinterpret_cast<uint32_t*>(w + c.off_barrier);
+  partition_coop_kernel<<<c.tiles, kPartThreads, 0, st>>>(a);
+  LSS_LAUNCH_CHECK("partition_coop_kernel");
+  LocalArgs l;
+  memset(&l, 0, sizeof(l));
+  l.keys = a.part_keys; l.vals = a.part_vals; l.bucket_start = a.bucket_start;
+  l.sorted_points = sorted_points; l.sorted_ranks = nullptr; l.sorted_cells = sorted_cells;
+  l.cell_range = reinterpret_cast<int2*>(cell_range); l.counts = counts;
+  l.g = g;
+  l.div_b = FastDiv(g.B); l.div_z = FastDiv(g.nx[2]); l.div_y = FastDiv(g.nx[1]);
+  l.lo_bits = c.lo_bits;
+  return launch_local_sort(l, c.n_buckets, st);
+}
+
 template <int kLanes>
 static int launch_bwd(const PoolBwdArgs& a, int blocks, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) {
@@ -306,11 +388,14 @@ int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* 
   a.feat_t = reinterpret_cast<const float4*>(d_feat_t); a.cells = d_cells;
   a.ddepth = d_ddepth; a.dfeat = d_dfeat;
   a.D = shape->D; a.fH = shape->fH; a.fW = shape->fW; a.C = shape->C; a.G = shape->C / 4;
-  const size_t smem = ((size_t)2 * a.D * a.fW + (size_t)a.C * (a.fW + 1)) * 4;
+  const int G = a.G;
+  const int lanes = G <= 4 ? 4 : G <= 8 ? 8 : G <= 16 ? 16 : 32;
+  const int round = (32 / lanes) * (lanes >= 8 ? 8 : lanes);   // depth bins per kernel round
+  const int Dpad = (a.D + round - 1) / round * round;
+  const size_t smem = ((size_t)3 * Dpad * a.fW + (size_t)a.C * (a.fW + 1)) * 4;
   LSS_REQUIRE(smem <= 200 * 1024, LSS_ERR_UNSUPPORTED);
   const int blocks = shape->B * shape->N * shape->fH;
   cudaStream_t st = as_stream(stream);
-  const int G = a.G;
   if (G <= 4) return launch_bwd<4>(a, blocks, smem, st);
   if (G <= 8) return launch_bwd<8>(a, blocks, smem, st);
   if (G <= 16) return launch_bwd<16>(a, blocks, smem, st);
@@ -324,7 +409,9 @@ size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid) {
   if (make_grid(grid, shape->B, &g) != LSS_OK) return 0;
   const long long P = shape_points(shape);
   const SortPlan s = make_sort_plan(P, g.n_cells);
-  return make_msd_plan(s).total_bytes + 2 * align_up((size_t)P * 4, 256);
+  const size_t general = make_msd_plan(s).total_bytes + 2 * align_up((size_t)P * 4, 256);
+  const size_t coop = make_coop_plan(P, g.n_cells, shape->D * shape->fH * shape->fW, false).total_bytes;
+  return general > coop ? general : coop;
 }
 
 int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
@@ -345,7 +432,9 @@ int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, cons
   const long long P = shape_points(shape);
   const SortPlan s = make_sort_plan(P, g.n_cells);
   const size_t ws_sort = make_msd_plan(s).total_bytes;
-  const size_t need = ws_sort + 2 * align_up((size_t)P * 4, 256);
+  const CoopPlan coop = make_coop_plan(P, g.n_cells, shape->D * shape->fH * shape->fW, true);
+  size_t need = ws_sort + 2 * align_up((size_t)P * 4, 256);
+  if (coop.total_bytes > need) need = coop.total_bytes;
   LSS_REQUIRE(workspace_bytes >= need, LSS_ERR_WORKSPACE_TOO_SMALL);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(d_workspace);
@@ -359,6 +448,9 @@ int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, cons
   ga.rots = d_rots; ga.intrins = d_intrins; ga.post_rots = d_post_rots;
   ga.raw = 1; ga.N = shape->N; ga.D = shape->D; ga.fH = shape->fH; ga.fW = shape->fW;
   const int ppc = shape->D * shape->fH * shape->fW;
+  if (coop.ok)  // all tiles co-resident: K0 + K1' + partition in one kernel, then local sort + intervals
+    return run_coop_plan(coop, ga, g, P, d_cells, d_sorted_points, d_sorted_cells, d_cell_range, d_counts,
+                         d_workspace, st);
   const MsdPlan msd = make_msd_plan(s);
   if (msd.ok && (kSortTile - 1) / ppc + 2 <= kSmallMaxCams) {
     // single wave: P1 = K0 + K1' + MSD partition, P2 = local sort + intervals (K2 + K3)
@@ -386,5 +478,11 @@ int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, cons
                           reinterpret_cast<uint32_t*>(w + s.off_control),
                           (long long)(s.control_bytes / 4), st);
 }
+
+#ifdef LSS_PHASE_TIMING
+int lss_debug_phase_ts(int kernel, unsigned long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_phase_ts, (size_t)n * 8, (size_t)kernel * 4096 * 8 * 8);
+}
+#endif
 
 }  // extern "C"

@@ -109,7 +109,33 @@ inline int make_grid(const LssGrid* g, int32_t B, GridDev* out) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Optional phase timestamps (build with -DLSS_PHASE_TIMING; tools/phase_timing.py reads them).
+#ifdef LSS_PHASE_TIMING
+__device__ unsigned long long g_phase_ts[2][4096 * 8];
+__device__ __forceinline__ void phase_stamp(int kernel, int slot) {
+  if (threadIdx.x == 0 && blockIdx.x < 4096) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_phase_ts[kernel][blockIdx.x * 8 + slot] = t;
+  }
+}
+#else
+__device__ __forceinline__ void phase_stamp(int, int) {}
+#endif
+
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
+
+// 128-bit read-only load that the compiler may not sink towards its first use: a batch of these
+// stays a batch, i.e. all of them are in flight before the first result is consumed.
+__device__ __forceinline__ float4 ldg_f4_issue(const float4* p, bool pred) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "l"(p), "r"(static_cast<int>(pred)));
+  return v;
+}
 
 // streaming 128-bit store: the BEV map is written once and not re-read by us
 __device__ __forceinline__ void st_stream_f4(float4* p, float4 v) { __stcs(p, v); }

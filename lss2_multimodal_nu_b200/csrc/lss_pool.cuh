@@ -180,6 +180,11 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
   }
 
   // ---- REDUCE: segmented sums over the sorted points --------------------------
+  // A group of kLanes lanes owns the intervals that START inside its chunk of kLanes sorted
+  // points.  Per chunk: one cooperative load (point id, output cell, depth), the decoded
+  // records go to shared memory, and the walk reads them back with one broadcast LDS.128 per
+  // point.  The tail of the last interval is followed into the next chunk in steps of 4 points.
+  __shared__ int4 s_rec[kPoolWarps][32];
   const int rw = warp - a.fill_warps, n_rw = kPoolWarps - a.fill_warps;
   const int grp = lane / kLanes, sub = lane % kLanes;
   const uint32_t gmask = (kLanes == 32) ? 0xffffffffu : (((1u << kLanes) - 1u) << (grp * kLanes));
@@ -188,16 +193,19 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
   const int slot = (blockIdx.x * n_rw + rw) * kGroups + grp;
   const int n_slots = gridDim.x * n_rw * kGroups;
   const bool lane_active = sub < a.G;  // kLanes may exceed G (e.g. C = 80: 20 of 32 lanes)
+  int4* rec = &s_rec[warp][grp * kLanes];
+  const float4* src = kFused ? a.feat_t : a.x;
 
   for (int chunk = slot; chunk < n_chunks; chunk += n_slots) {
     int base = chunk * kLanes;
+    int width = kLanes;      // points loaded per pass: a full chunk first, then 4 at a time
     int cur_cell = -1;
     float4 acc = zero4;
     bool first = true;
     while (true) {
-      // cooperative load of kLanes consecutive sorted points
+      // cooperative load of `width` consecutive sorted points
       const int i = base + sub;
-      const bool valid = i < K;
+      const bool valid = (sub < width) && (i < K);
       const int32_t pt = valid ? __ldg(a.sorted_points + i) : 0;
       const int32_t cell = valid ? __ldg(a.sorted_cells + i) : -1;
       int32_t prev = __shfl_up_sync(gmask, cell, 1, kLanes);
@@ -215,45 +223,42 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
         row = static_cast<uint32_t>(pt);
         dv = 1.f;
       }
+      __syncwarp(gmask);   // the previous pass is done reading the records
+      rec[sub] = make_int4(cell, head ? 1 : 0, static_cast<int>(row), __float_as_int(dv));
+      __syncwarp(gmask);
       bool done = false;
-#pragma unroll
-      for (int j0 = 0; j0 < kLanes; j0 += 4) {
-        if (done) break;
-        int32_t cj[4];
-        bool hj[4];
-        float dj[4];
+      for (int j0 = 0; j0 < width; j0 += 4) {
+        int4 r[4];
         float4 fj[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int j = j0 + u;
-          cj[u] = __shfl_sync(gmask, cell, j, kLanes);
-          hj[u] = __shfl_sync(gmask, head ? 1 : 0, j, kLanes) != 0;
-          dj[u] = __shfl_sync(gmask, dv, j, kLanes);
-          const uint32_t rj = __shfl_sync(gmask, row, j, kLanes);
-          const float4* src = kFused ? a.feat_t : a.x;
-          fj[u] = (cj[u] >= 0 && lane_active) ? ldg_f4(src + (size_t)rj * a.G + sub) : zero4;
+          r[u] = rec[j0 + u];
+          fj[u] = ldg_f4_issue(src + (size_t)static_cast<uint32_t>(r[u].z) * a.G + sub, r[u].x >= 0 && lane_active);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (done) break;
-          if (cj[u] < 0) { done = true; break; }            // ran off the end of the kept points
-          if (hj[u]) {
-            if (!first) { done = true; break; }              // next group's interval starts here
+          if (r[u].x < 0) { done = true; break; }             // ran off the end of the kept points
+          if (r[u].y) {
+            if (!first) { done = true; break; }                // the next group's interval starts here
             if (cur_cell >= 0 && lane_active) st_stream_f4(a.bev + (size_t)cur_cell * a.G + sub, acc);
             acc = zero4;
-            cur_cell = cj[u];
+            cur_cell = r[u].x;
           }
           if (cur_cell >= 0) {
-            acc.x = fmaf(dj[u], fj[u].x, acc.x);
-            acc.y = fmaf(dj[u], fj[u].y, acc.y);
-            acc.z = fmaf(dj[u], fj[u].z, acc.z);
-            acc.w = fmaf(dj[u], fj[u].w, acc.w);
+            const float d = __int_as_float(r[u].w);
+            acc.x = fmaf(d, fj[u].x, acc.x);
+            acc.y = fmaf(d, fj[u].y, acc.y);
+            acc.z = fmaf(d, fj[u].z, acc.z);
+            acc.w = fmaf(d, fj[u].w, acc.w);
           }
         }
+        if (done) break;
       }
       if (done || cur_cell < 0) break;   // closed by a foreign head / end, or no interval started here
-      first = false;                     // keep following the open interval into the next chunk
-      base += kLanes;
+      first = false;                     // keep following the open interval
+      base += width;
+      width = 4;
     }
     if (cur_cell >= 0 && lane_active) st_stream_f4(a.bev + (size_t)cur_cell * a.G + sub, acc);
   }
@@ -305,22 +310,31 @@ struct PoolBwdArgs {
 };
 
 template <int kLanes>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256, 3)
 liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
-  extern __shared__ float s_mem[];
+  extern __shared__ __align__(16) unsigned char s_raw[];
   constexpr int kPts = 32 / kLanes;                 // points per warp step
   constexpr int kUnroll = kLanes >= 8 ? 8 : kLanes; // steps in flight
+  constexpr int kRound = kPts * kUnroll;            // depth bins per round
   constexpr int kLog = kLanes == 32 ? 5 : kLanes == 16 ? 4 : kLanes == 8 ? 3 : 2;
   constexpr int kLogU = kUnroll == 8 ? 3 : 2;
   const int bn = blockIdx.x / a.fH, h = blockIdx.x % a.fH;
   const int HW = a.fH * a.fW;
-  int32_t* s_cells = reinterpret_cast<int32_t*>(s_mem);  // [D][fW]
-  float* s_dd = s_mem + a.D * a.fW;                       // [D][fW]
-  float* s_df = s_dd + a.D * a.fW;                        // [C][fW+1]
+  // depth bins are padded to a whole number of rounds ({-1, 0} = dropped point), so the
+  // main loop needs no bounds checks at all
+  const int Dpad = (a.D + kRound - 1) / kRound * kRound;
+  int2* s_cd = reinterpret_cast<int2*>(s_raw);            // [Dpad][fW] {output cell, depth bits}
+  float* s_dd = reinterpret_cast<float*>(s_cd + Dpad * a.fW);  // [Dpad][fW]
+  float* s_df = s_dd + Dpad * a.fW;                       // [C][fW+1]
   const int dfs = a.fW + 1;
-  for (int i = threadIdx.x; i < a.D * a.fW; i += blockDim.x) {
+  for (int i = threadIdx.x; i < Dpad * a.fW; i += blockDim.x) {
     const int d = i / a.fW, w = i - d * a.fW;
-    s_cells[i] = __ldg(a.cells + ((size_t)(bn * a.D + d) * a.fH + h) * a.fW + w);
+    int2 v = make_int2(-1, 0);
+    if (d < a.D) {
+      v.x = __ldg(a.cells + ((size_t)(bn * a.D + d) * a.fH + h) * a.fW + w);
+      v.y = __float_as_int(__ldg(a.depth_t + ((size_t)bn * HW + h * a.fW + w) * a.D + d));
+    }
+    s_cd[i] = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -333,28 +347,34 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
   for (int k = 0; k < kLogU; ++k)
     if (sub & (kLanes >> (k + 1))) my_u += kUnroll >> (k + 1);
   const bool writer = (sub & ((kLanes >> kLogU) - 1)) == 0;
+  const float4* gbase = a.dbev + sub;                 // this lane's float4 column of every voxel line
+  const uint32_t G = static_cast<uint32_t>(a.G);
+  const int step = kPts * a.fW;                       // shared-memory stride between unrolled steps
 
   for (int w = warp; w < a.fW; w += nwarps) {
-    const size_t pix = (size_t)bn * HW + h * a.fW + w;
-    const float4 f = lane_active ? ldg_f4(a.feat_t + pix * a.G + sub) : zero4;
+    const uint32_t pix = static_cast<uint32_t>(bn * HW + h * a.fW + w);
+    const float4 f = lane_active ? ldg_f4(a.feat_t + pix * G + sub) : zero4;
+    const double fx = f.x, fy = f.y, fz = f.z, fw = f.w;
     float4 acc = zero4;
-    for (int d0 = 0; d0 < a.D; d0 += kPts * kUnroll) {
+    const int2* cd = s_cd + grp * a.fW + w;
+    float* dd = s_dd + (my_u * kPts + grp) * a.fW + w;
+    for (int d0 = 0; d0 < Dpad; d0 += kRound, cd += kRound * a.fW, dd += kRound * a.fW) {
       float4 g[kUnroll];
       float dv[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const int d = d0 + u * kPts + grp;
-        const int32_t cell = (d < a.D) ? s_cells[d * a.fW + w] : -1;
-        dv[u] = (d < a.D) ? __ldg(a.depth_t + pix * a.D + d) : 0.f;
-        g[u] = (cell >= 0 && lane_active) ? ldg_f4(a.dbev + (size_t)cell * a.G + sub) : zero4;
+        const int2 v = cd[u * step];
+        dv[u] = __int_as_float(v.y);
+        const uint32_t off = static_cast<uint32_t>(v.x) * G;   // n_cells * G < 2^31 (checked by the host)
+        g[u] = (v.x >= 0 && lane_active) ? ldg_f4(gbase + off) : zero4;
       }
       double dot[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        double t = static_cast<double>(g[u].x) * static_cast<double>(f.x);
-        t = fma(static_cast<double>(g[u].y), static_cast<double>(f.y), t);
-        t = fma(static_cast<double>(g[u].z), static_cast<double>(f.z), t);
-        t = fma(static_cast<double>(g[u].w), static_cast<double>(f.w), t);
+        double t = static_cast<double>(g[u].x) * fx;
+        t = fma(static_cast<double>(g[u].y), fy, t);
+        t = fma(static_cast<double>(g[u].z), fz, t);
+        t = fma(static_cast<double>(g[u].w), fw, t);
         dot[u] = t;
         acc.x = fmaf(dv[u], g[u].x, acc.x);
         acc.y = fmaf(dv[u], g[u].y, acc.y);
@@ -378,8 +398,7 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
           dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
         }
       }
-      const int d = d0 + my_u * kPts + grp;
-      if (writer && d < a.D) s_dd[d * a.fW + w] = static_cast<float>(dot[0]);
+      if (writer) *dd = static_cast<float>(dot[0]);   // rows beyond D are padding
     }
     // fold the kPts point-groups of the warp together
 #pragma unroll
@@ -390,10 +409,8 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
       acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
     if (grp == 0 && lane_active) {
-      s_df[(sub * 4 + 0) * dfs + w] = acc.x;
-      s_df[(sub * 4 + 1) * dfs + w] = acc.y;
-      s_df[(sub * 4 + 2) * dfs + w] = acc.z;
-      s_df[(sub * 4 + 3) * dfs + w] = acc.w;
+      float* df = s_df + (sub * 4) * dfs + w;
+      df[0] = acc.x; df[dfs] = acc.y; df[2 * dfs] = acc.z; df[3 * dfs] = acc.w;
     }
   }
   __syncthreads();

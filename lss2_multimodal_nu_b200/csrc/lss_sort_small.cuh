@@ -347,6 +347,7 @@ local_sort_intervals_kernel(LocalArgs a) {
   __shared__ uint32_t s_start[kLocalMaxBins];  // counts, then running start per bin
   __shared__ uint32_t s_warp_tot[kLocalWarps];
   __shared__ int s_kv[2];
+  extern __shared__ int32_t s_cell[];  // [nbins] output cell of each bin's rank (dynamic)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbins = 1 << a.lo_bits;
@@ -354,6 +355,7 @@ local_sort_intervals_kernel(LocalArgs a) {
   const int bucket = blockIdx.x;
   const uint32_t begin = a.bucket_start[bucket], end = a.bucket_start[bucket + 1];
   const uint32_t n = end - begin;
+  phase_stamp(1, 0);
 
   for (int i = tid; i < nbins; i += kLocalThreads) s_start[i] = 0;
   {
@@ -364,18 +366,25 @@ local_sort_intervals_kernel(LocalArgs a) {
   if (tid < 2) s_kv[tid] = 0;
   __syncthreads();
 
+  phase_stamp(1, 1);
   // ---- sweep 1: low-digit histogram of the bucket (keys of the first chunk stay in registers)
-  int32_t key[kLocalItems];
+  int32_t key[kLocalItems], val[kLocalItems];
 #pragma unroll
   for (int j = 0; j < kLocalItems; ++j) {
     const uint32_t i = warp * (32 * kLocalItems) + j * 32 + lane;
     key[j] = (i < n) ? a.keys[begin + i] : 0;
+    val[j] = (i < n) ? a.vals[begin + i] : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < kLocalItems; ++j) {
+    const uint32_t i = warp * (32 * kLocalItems) + j * 32 + lane;
     if (i < n) atomicAdd(&s_start[static_cast<uint32_t>(key[j]) & mask], 1u);
   }
   for (uint32_t i = kLocalChunk + tid; i < n; i += kLocalThreads)
     atomicAdd(&s_start[static_cast<uint32_t>(a.keys[begin + i]) & mask], 1u);
   __syncthreads();
 
+  phase_stamp(1, 2);
   // ---- exclusive scan over bins; every bin is one rank, i.e. one cell: write its interval
   {
     const int per = nbins >= kLocalThreads ? nbins / kLocalThreads : 1;
@@ -405,6 +414,7 @@ local_sort_intervals_kernel(LocalArgs a) {
       if (k < per && bin < nbins) {
         s_start[bin] = run;
         const int32_t r = static_cast<int32_t>((static_cast<uint32_t>(bucket) << a.lo_bits) | static_cast<uint32_t>(bin));
+        s_cell[bin] = -1;
         if (r < a.g.n_cells) {
           // rank = ((x*Y + y)*Z + z)*B + b  ->  output cell ((b*X + x)*Y + y)*Z + z
           uint32_t t0, b, t1, z, x, y;
@@ -413,6 +423,7 @@ local_sort_intervals_kernel(LocalArgs a) {
           a.div_y.divmod(t1, x, y);
           const int32_t cell = ((static_cast<int32_t>(b) * a.g.nx[0] + static_cast<int32_t>(x)) * a.g.nx[1] +
                                 static_cast<int32_t>(y)) * a.g.nx[2] + static_cast<int32_t>(z);
+          s_cell[bin] = cell;
           const int s0 = static_cast<int>(begin + run);
           a.cell_range[cell] = local[k] ? make_int2(s0, s0 + static_cast<int>(local[k])) : make_int2(0, 0);
           kept += static_cast<int>(local[k]);
@@ -430,6 +441,7 @@ local_sort_intervals_kernel(LocalArgs a) {
   }
   __syncthreads();
   if (tid < 2 && s_kv[tid]) atomicAdd(&a.counts[tid], s_kv[tid]);
+  phase_stamp(1, 3);
   if (n == 0) return;
 
   // ---- sweep 2: stable rank + scatter, chunk by chunk (ascending input order) ----
@@ -439,6 +451,7 @@ local_sort_intervals_kernel(LocalArgs a) {
       for (int j = 0; j < kLocalItems; ++j) {
         const uint32_t i = c0 + warp * (32 * kLocalItems) + j * 32 + lane;
         key[j] = (i < n) ? a.keys[begin + i] : 0;
+        val[j] = (i < n) ? a.vals[begin + i] : 0;
       }
     }
     uint16_t offs[kLocalItems];
@@ -483,18 +496,12 @@ local_sort_intervals_kernel(LocalArgs a) {
       if (i < n) {
         const uint32_t digit = static_cast<uint32_t>(key[j]) & mask;
         const uint32_t dst = begin + s_start[digit] + s_wh[warp][digit] + offs[j];
-        a.sorted_points[dst] = a.vals[begin + i];
+        a.sorted_points[dst] = val[j];
         if (a.sorted_ranks) a.sorted_ranks[dst] = key[j];
-        {
-          uint32_t t0, b, t1, z, x, y;
-          a.div_b.divmod(static_cast<uint32_t>(key[j]), t0, b);
-          a.div_z.divmod(t0, t1, z);
-          a.div_y.divmod(t1, x, y);
-          a.sorted_cells[dst] = ((static_cast<int32_t>(b) * a.g.nx[0] + static_cast<int32_t>(x)) * a.g.nx[1] +
-                                 static_cast<int32_t>(y)) * a.g.nx[2] + static_cast<int32_t>(z);
-        }
+        a.sorted_cells[dst] = s_cell[digit];
       }
     }
+    phase_stamp(1, 4 + (c0 ? 1 : 0));
     if (c0 + kLocalChunk < n) {  // more chunks: advance the bin starts, clear the warp counters
       __syncthreads();
 #pragma unroll
@@ -510,6 +517,19 @@ local_sort_intervals_kernel(LocalArgs a) {
       __syncthreads();
     }
   }
+}
+
+inline int launch_local_sort(const LocalArgs& l, int n_buckets, cudaStream_t st) {
+  const size_t dyn = (size_t)(1 << l.lo_bits) * sizeof(int32_t);
+  static bool attr_set = false;
+  if (!attr_set) {  // static (41 KB) + dynamic (<= 8 KB) may exceed the 48 KB default
+    LSS_CUDA_TRY(cudaFuncSetAttribute(local_sort_intervals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kLocalMaxBins * sizeof(int32_t))), "cudaFuncSetAttribute(local sort)");
+    attr_set = true;
+  }
+  local_sort_intervals_kernel<<<n_buckets, kLocalThreads, dyn, st>>>(l);
+  LSS_LAUNCH_CHECK("local_sort_intervals_kernel");
+  return LSS_OK;
 }
 
 struct MsdPlan {
@@ -567,9 +587,7 @@ inline int run_msd_plan(const SortPlan& s, const MsdPlan& m, const SmallGeom& sg
   l.g = sg.grid;
   l.div_b = FastDiv(sg.grid.B); l.div_z = FastDiv(sg.grid.nx[2]); l.div_y = FastDiv(sg.grid.nx[1]);
   l.lo_bits = m.lo_bits;
-  local_sort_intervals_kernel<<<m.n_buckets, kLocalThreads, 0, st>>>(l);
-  LSS_LAUNCH_CHECK("local_sort_intervals_kernel");
-  return LSS_OK;
+  return launch_local_sort(l, m.n_buckets, st);
 }
 
 }  // namespace lss
