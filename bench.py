@@ -186,123 +186,70 @@ def run_ours(args, cfg):
     _abi.load()
 
     # ---- per-rank inputs: `sets` independent batches so the working set exceeds L2 -------
+    from lss2_multimodal_nu_b200.pipeline import LiftSplatStep, HostPipeline
     grid = F.GridSpec.from_bounds(cfg.xbound, cfg.ybound, cfg.zbound)
-    frustum_t = None
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import lss_oracle as O   # only for the frustum axes tables + cpu_baseline (never timed as product)
+    import lss_oracle as O   # frustum axis tables + cpu_baseline only (never the timed product path)
     us, vs, ds = (torch.from_numpy(a).to(dev) for a in O.frustum_axes(cfg.final_dim, cfg.downsample, cfg.dbound))
-    X, Y, Z = grid.nx
     C = cfg.C
-    shape = _abi.make_shape(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, C)
-    g = grid.c()
-    P = cfg.P
-    BN, HW = cfg.B * cfg.N, cfg.fH * cfg.fW
-    host, sets = [], []
+    stream = torch.cuda.Stream(dev)
+    host, steps = [], []
     for s in range(args.sets):
         seed = shard.rank_seed(1234, rank, s)
         cal = S.make_calibration(cfg, seed); ft = S.make_features(cfg, seed)
         h = {k: torch.from_numpy(v).pin_memory() for k, v in {**cal, **ft}.items()}
         host.append(h)
-        d = {k: v.to(dev) for k, v in h.items()}
+        st_ = LiftSplatStep(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, C, grid, us, vs, ds, device=dev,
+                            capture=not args.no_graph, stream=stream)
+        st_.load(h)
         gen = torch.Generator(device=dev); gen.manual_seed(seed)
-        d["dbev"] = torch.randn((cfg.B, X, Y, Z * C), device=dev, generator=gen)   # channels-innermost
-        d["cells"] = torch.empty(P, dtype=torch.int32, device=dev)
-        d["sorted_points"] = torch.empty(P, dtype=torch.int32, device=dev)
-        d["sorted_cells"] = torch.empty(P, dtype=torch.int32, device=dev)
-        d["cell_range"] = torch.empty((grid.n_cells(cfg.B), 2), dtype=torch.int32, device=dev)
-        d["counts"] = torch.empty(2, dtype=torch.int32, device=dev)
-        d["depth_t"] = torch.empty((BN * HW, cfg.D), device=dev)
-        d["feat_t"] = torch.empty((BN * HW, C), device=dev)
-        d["bev"] = torch.empty((cfg.B, X, Y, Z * C), device=dev)
-        d["ddepth"] = torch.empty((BN, cfg.D, cfg.fH, cfg.fW), device=dev)
-        d["dfeat"] = torch.empty((BN, C, cfg.fH, cfg.fW), device=dev)
-        sets.append(d)
-    ws_bytes = _abi.load().lss_plan_workspace_bytes(shape, g)
-    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
-    p = lambda t: t.data_ptr()
+        st_._dbev.copy_(torch.randn(st_._dbev.shape, device=dev, generator=gen))
+        steps.append(st_)
+    torch.cuda.synchronize()
+    KERNELS_PER_STEP = steps[0].kernels_per_step
 
-    def k_plan(d, st):
-        _abi.call("lss_build_plan", p(us), p(vs), p(ds), p(d["rots"]), p(d["trans"]), p(d["intrins"]),
-                  p(d["post_rots"]), p(d["post_trans"]), g, shape, p(d["cells"]), p(d["sorted_points"]),
-                  p(d["sorted_cells"]), p(d["cell_range"]), p(d["counts"]), p(ws), ws_bytes, st)
+    def run_step(i):
+        steps[i % len(steps)].run()
 
-    def k_stage(d, st):
-        _abi.call("lss_lift_stage", p(d["depth"]), p(d["feat"]), shape, p(d["depth_t"]), p(d["feat_t"]), st)
-
-    def k_fwd(d, st):
-        _abi.call("lss_liftsplat_fwd", p(d["depth_t"]), p(d["feat_t"]), p(d["sorted_points"]),
-                  p(d["sorted_cells"]), p(d["cell_range"]), p(d["counts"]), g, shape,
-                  _abi.LSS_BEV_NHWC, p(d["bev"]), st)
-
-    def k_bwd(d, st):
-        _abi.call("lss_liftsplat_bwd", p(d["dbev"]), p(d["depth_t"]), p(d["feat_t"]), p(d["cells"]), g,
-                  shape, _abi.LSS_BEV_NHWC, p(d["ddepth"]), p(d["dfeat"]), st)
-
-    def step(d, st):
-        k_plan(d, st); k_stage(d, st); k_fwd(d, st); k_bwd(d, st)
-
-    KERNELS_PER_STEP = 4 + 1 + 1 + 1   # geometry, 2 sort passes, intervals | stage | fwd | bwd
-
-    stream = torch.cuda.Stream(dev)
-    graphs = None
-    with torch.cuda.stream(stream):
-        st = stream.cuda_stream
-        for d in sets:                      # un-captured warm run (module load, attribute setup)
-            step(d, st)
+    def barrier():
         stream.synchronize()
-        if not args.no_graph:
-            graphs = []
-            for d in sets:
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=stream):
-                    step(d, torch.cuda.current_stream().cuda_stream)
-                graphs.append(gr)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-        def run_step(i):
-            if graphs is not None:
-                graphs[i % len(graphs)].replay()
-            else:
-                step(sets[i % len(sets)], st)
+    for i in range(max(3, args.warmup)):
+        run_step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        run_step(i)
+    e1.record(stream)
+    stream.synchronize()
+    clocks.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    barrier()
+    value = shard.aggregate_throughput(cfg.B * args.steps, elapsed_ms, dev)   # all samples / slowest rank
+    elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
+    ms_per_step = elapsed_ms / args.steps
 
-        def barrier():
-            stream.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        for i in range(max(3, args.warmup)):
-            run_step(i)
-        barrier()
-        clocks = ClockSampler(local)
-        clocks.start()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(args.steps):
-            run_step(i)
-        e1.record(stream)
-        stream.synchronize()
-        clocks.stop()
-        elapsed_ms = e0.elapsed_time(e1)
-        barrier()
-        value = shard.aggregate_throughput(cfg.B * args.steps, elapsed_ms, dev)   # all samples / slowest rank
-        elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
-        ms_per_step = elapsed_ms / args.steps
-
-        # ---- per-kernel timing (CUDA events on the launching stream), cold rotating sets ----
-        def time_kernel(fn, n):
-            evs = []
+    # ---- per-kernel timing (CUDA events on the launching stream), cold rotating sets ----
+    def time_kernel(name, n):
+        evs = []
+        with torch.cuda.stream(stream):
             for i in range(n):
-                d = sets[i % len(sets)]
+                d = steps[i % len(steps)]
                 a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                a.record(stream); fn(d, st); b.record(stream)
+                a.record(stream); getattr(d, "enqueue_" + name)(stream.cuda_stream); b.record(stream)
                 evs.append((a, b))
-            stream.synchronize()
-            ts = sorted(a.elapsed_time(b) for a, b in evs)
-            return {"mean_us": 1e3 * sum(ts) / len(ts), "median_us": 1e3 * ts[len(ts) // 2], "min_us": 1e3 * ts[0]}
+        stream.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return {"mean_us": 1e3 * sum(ts) / len(ts), "median_us": 1e3 * ts[len(ts) // 2], "min_us": 1e3 * ts[0]}
 
-        n_k = min(args.steps, 200)
-        kt = {"plan": time_kernel(k_plan, n_k), "stage": time_kernel(k_stage, n_k),
-              "fwd": time_kernel(k_fwd, n_k), "bwd": time_kernel(k_bwd, n_k)}
+    n_k = min(args.steps, 200)
+    kt = {k: time_kernel(k, n_k) for k in ("plan", "stage", "fwd", "bwd")}
 
     # ---- roofline of the dominant kernel (fused forward) -----------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -329,43 +276,42 @@ def run_ours(args, cfg):
                 "step_frac_of_hbm_roofline": (alg["total"] / (ms_per_step * 1e-3) / 1e9) / peak,
                 "kernels_us": {k: round(v["mean_us"], 2) for k, v in kt.items()}}
 
-    # ---- e2e: public API, host buffers ----------------------------------------------------
-    e2e_steps = args.e2e_steps or min(args.steps, 100)
-    hb = sum(v.numel() * v.element_size() for v in host[0].values())
-    out_host = [(torch.empty((BN, cfg.D, cfg.fH, cfg.fW)).pin_memory(),
-                 torch.empty((BN, C, cfg.fH, cfg.fW)).pin_memory()) for _ in range(2)]
-    db = sum(t.numel() * t.element_size() for t in out_host[0])
-    CAL = ("rots", "trans", "intrins", "post_rots", "post_trans")
+    # ---- e2e: HostPipeline (public API), pinned host buffers, two steps in flight ----------
+    e2e_steps = args.e2e_steps or min(args.steps, 200)
+    pipe = HostPipeline(lambda: LiftSplatStep(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, C, grid, us, vs, ds,
+                                              device=dev, capture=not args.no_graph), depth=2)
+    for sl in pipe.slots:   # the upstream gradient is produced on the device by the downstream network
+        sl["step"]._dbev.copy_(steps[0]._dbev)
+    torch.cuda.synchronize()
+    checksum = 0.0
+    # the host-side "dataset": one pinned block per batch set, laid out as the step consumes it
+    host_blocks = [pipe.pack(h) for h in host]
 
-    def e2e_step(i):
-        h = host[i % len(host)]
-        dbev = sets[i % len(sets)]["dbev"].permute(0, 3, 1, 2)   # produced on device by the downstream net
-        t = {k: h[k].to(dev, non_blocking=True) for k in h}
-        depth = t["depth"].requires_grad_(True); feat = t["feat"].requires_grad_(True)
-        plan = F.build_plan(us, vs, ds, *(t[k] for k in CAL), grid)
-        bev = F.lift_splat(depth, feat, plan)
-        bev.backward(dbev)
-        o = out_host[i % 2]
-        o[0].copy_(depth.grad, non_blocking=True); o[1].copy_(feat.grad, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the step's result is on the host
+    def e2e_run(n):
+        nonlocal checksum
+        for i in range(n):
+            if pipe.in_flight() == len(pipe.slots):
+                out = pipe.collect()
+                checksum += float(out["d_depth"][0, 0, 0, 0])     # the host really reads the result
+            pipe.submit(host_blocks[i % len(host_blocks)])
+        while pipe.in_flight():
+            out = pipe.collect()
+            checksum += float(out["d_depth"][0, 0, 0, 0])
 
-    for i in range(3):
-        e2e_step(i)
+    e2e_run(4)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    b.record()
+    t0 = time.perf_counter()
+    e2e_run(e2e_steps)
     torch.cuda.synchronize()
-    e2e_ms = a.elapsed_time(b)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e_value = shard.aggregate_throughput(cfg.B * e2e_steps, e2e_ms, dev)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hb,
-           "d2h_bytes_per_step": db, "steps": e2e_steps,
-           "note": "public API (build_plan + lift_splat autograd), pinned host depth/feat/calibration in, "
-                   "d_depth/d_feat out, per-step stream sync; upstream dBEV stays on the device"}
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
+           "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+           "note": "pipeline.HostPipeline: pinned host calibration+depth+feat in (one packed H2D), "
+                   "d_depth+d_feat out (one packed D2H), every step's result read on the host, two steps "
+                   "in flight (copies overlap kernels); upstream dBEV stays on the device; host wall clock"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -376,7 +322,7 @@ def run_ours(args, cfg):
                    "bev_layout": "channels_last (NHWC storage of the logical (B,C*Z,X,Y) map)",
                    "l2": "inputs larger than L2: %d rotating batch sets (%.0f MB BEV+dBEV each)"
                          % (args.sets, 2 * alg["bev"] / 1e6),
-                   "launch": "cuda-graph replay" if graphs is not None else "stream launches",
+                   "launch": "stream launches" if args.no_graph else "cuda-graph replay (lift staging || plan)",
                    "step": "camera prep+geometry+sort+intervals, lift staging, fused fwd, fused bwd"},
         "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
         "gpu_launches": KERNELS_PER_STEP * args.steps,

@@ -1,4 +1,6 @@
 // extern "C" entry points declared in include/lss_b200.h.
+#include <stdlib.h>
+
 #include "lss_common.cuh"
 #include "lss_geometry.cuh"
 #include "lss_pool.cuh"
@@ -304,10 +306,16 @@ static int pool_fwd_common(bool fused, const float* d_depth_t, const float* d_fe
   a.n_cells = (uint32_t)g.n_cells;
   a.G = C / 4; a.D = D; a.HW = HW;
   LSS_REQUIRE((long long)g.n_cells * a.G < (1ll << 31), LSS_ERR_BAD_DIMENSION);
-  a.fill_warps = 3;
+  a.fill_warps = 1;
+  int blocks_per_sm = 12;
+  if (const char* e = getenv("LSS_FILL_WARPS")) a.fill_warps = atoi(e);          // tuning knobs
+  if (const char* e = getenv("LSS_POOL_BLOCKS_PER_SM")) blocks_per_sm = atoi(e);
+  if (a.fill_warps < 1) a.fill_warps = 1;
+  if (a.fill_warps > kPoolWarps - 1) a.fill_warps = kPoolWarps - 1;
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
   a.div_g = FastDiv(a.G);
   a.div_dhw = FastDiv((uint32_t)(dhw > 0 ? dhw : 1)); a.div_hw = FastDiv((uint32_t)(HW > 0 ? HW : 1));
-  const int blocks = sm_count() * 6;
+  const int blocks = sm_count() * blocks_per_sm;
   return fused ? launch_pool_fwd<true>(a, blocks, st) : launch_pool_fwd<false>(a, blocks, st);
 }
 

@@ -111,7 +111,14 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // Optional phase timestamps (build with -DLSS_PHASE_TIMING; tools/phase_timing.py reads them).
 #ifdef LSS_PHASE_TIMING
-__device__ unsigned long long g_phase_ts[2][4096 * 8];
+__device__ unsigned long long g_phase_ts[3][4096 * 8];
+__device__ __forceinline__ void phase_stamp_any(int kernel, int slot) {   // caller picks the thread
+  if (blockIdx.x < 4096) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_phase_ts[kernel][blockIdx.x * 8 + slot] = t;
+  }
+}
 __device__ __forceinline__ void phase_stamp(int kernel, int slot) {
   if (threadIdx.x == 0 && blockIdx.x < 4096) {
     unsigned long long t;
@@ -120,6 +127,7 @@ __device__ __forceinline__ void phase_stamp(int kernel, int slot) {
   }
 }
 #else
+__device__ __forceinline__ void phase_stamp_any(int, int) {}
 __device__ __forceinline__ void phase_stamp(int, int) {}
 #endif
 
@@ -137,7 +145,46 @@ __device__ __forceinline__ float4 ldg_f4_issue(const float4* p, bool pred) {
   return v;
 }
 
-// streaming 128-bit store: the BEV map is written once and not re-read by us
+// L2 residency control.  The forward streams 82 MB of BEV through a 126 MB L2 while it keeps
+// re-reading ~9 MB of small tables (staged features, sorted points, intervals): the stream is
+// marked evict-first and the tables evict-last, so the tables stay resident instead of being
+// pushed out to HBM (where their reloads would queue behind the write-back traffic).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_f4_hint(float4* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+// streaming 128-bit store (no hint)
 __device__ __forceinline__ void st_stream_f4(float4* p, float4 v) { __stcs(p, v); }
+
+// predicated 128-bit read-only load with an L2 policy; like ldg_f4_issue it is not sunk
+__device__ __forceinline__ float4 ldg_f4_issue_hint(const float4* p, bool pred, uint64_t pol) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %6;\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "l"(p), "r"(static_cast<int>(pred)), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int32_t ldg_i32_hint(const int32_t* p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_f32_hint(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
 
 }  // namespace lss

@@ -150,14 +150,16 @@ template <bool kFused, int kLanes>
 __global__ void __launch_bounds__(kPoolThreads)
 pool_fwd_nhwc_kernel(PoolFwdArgs a) {
   constexpr int kGroups = 32 / kLanes;
+  constexpr uint32_t kLaneBits = (kLanes == 32) ? 0xffffffffu : ((1u << kLanes) - 1u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // ---- FILL: zeros into empty voxels (dedicated warps; pure stores that overlap the gathers) ----
+  // One coalesced load fetches the intervals of 32 consecutive cells (the next block of 32 is
+  // prefetched before the stores go out); the emptiness bits are shared with a ballot and the
+  // cells' 32*G float4 are covered by G full-warp stores.
   if (warp < a.fill_warps) {
-    // ---- FILL: zeros into empty voxels ------------------------------------
-    // One coalesced load fetches the intervals of 32 consecutive cells (the next block
-    // of 32 is prefetched before the stores go out); the emptiness bits are shared
-    // with a ballot and the cells' 32*G float4 are covered by G full-warp stores.
+    if (warp == 0 && lane == 0) phase_stamp_any(2, 0);
     const uint32_t n_fill = gridDim.x * static_cast<uint32_t>(a.fill_warps);
     uint32_t c0 = (blockIdx.x * a.fill_warps + warp) * 32u;
     int2 r = (c0 + lane < a.n_cells) ? __ldg(a.cell_range + c0 + lane) : make_int2(0, 1);
@@ -176,25 +178,32 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
       r = rn;
       c0 = c1;
     }
+    if (warp == 0 && lane == 0) phase_stamp_any(2, 1);
     return;
   }
 
   // ---- REDUCE: segmented sums over the sorted points --------------------------
   // A group of kLanes lanes owns the intervals that START inside its chunk of kLanes sorted
-  // points.  Per chunk: one cooperative load (point id, output cell, depth), the decoded
-  // records go to shared memory, and the walk reads them back with one broadcast LDS.128 per
-  // point.  The tail of the last interval is followed into the next chunk in steps of 4 points.
+  // points.  Per pass: one cooperative load (point id, output cell, depth); the decoded records
+  // {cell, feature-row offset, depth} go to shared memory and two group ballots (valid points,
+  // interval heads) drive the walk, which reads one broadcast LDS.128 per point and has no
+  // per-point bounds logic.  The tail of the last interval is followed into the next chunk in
+  // steps of 4 points, where it only accumulates up to the first foreign head.  The kernel is
+  // latency-bound (dependent gathers), so it is kept lean in registers: 8 CTAs stay resident
+  // per SM and supply the parallelism.
   __shared__ int4 s_rec[kPoolWarps][32];
   const int rw = warp - a.fill_warps, n_rw = kPoolWarps - a.fill_warps;
   const int grp = lane / kLanes, sub = lane % kLanes;
-  const uint32_t gmask = (kLanes == 32) ? 0xffffffffu : (((1u << kLanes) - 1u) << (grp * kLanes));
+  const uint32_t gmask = kLaneBits << (grp * kLanes);
   const int K = __ldg(a.counts);
   const int n_chunks = (K + kLanes - 1) / kLanes;
   const int slot = (blockIdx.x * n_rw + rw) * kGroups + grp;
   const int n_slots = gridDim.x * n_rw * kGroups;
   const bool lane_active = sub < a.G;  // kLanes may exceed G (e.g. C = 80: 20 of 32 lanes)
   int4* rec = &s_rec[warp][grp * kLanes];
-  const float4* src = kFused ? a.feat_t : a.x;
+  const float4* src_lane = (kFused ? a.feat_t : a.x) + sub;   // this lane's float4 column of a row
+  float4* bev_lane = a.bev + sub;
+  const uint32_t G = static_cast<uint32_t>(a.G);
 
   for (int chunk = slot; chunk < n_chunks; chunk += n_slots) {
     int base = chunk * kLanes;
@@ -224,43 +233,41 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
         dv = 1.f;
       }
       __syncwarp(gmask);   // the previous pass is done reading the records
-      rec[sub] = make_int4(cell, head ? 1 : 0, static_cast<int>(row), __float_as_int(dv));
+      rec[sub] = make_int4(cell, static_cast<int>(row * G), __float_as_int(dv), 0);
+      const uint32_t vbits = (__ballot_sync(gmask, valid) >> (grp * kLanes)) & kLaneBits;
+      const uint32_t hbits = (__ballot_sync(gmask, head) >> (grp * kLanes)) & kLaneBits;
       __syncwarp(gmask);
-      bool done = false;
-      for (int j0 = 0; j0 < width; j0 += 4) {
-        int4 r[4];
-        float4 fj[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          r[u] = rec[j0 + u];
-          fj[u] = ldg_f4_issue(src + (size_t)static_cast<uint32_t>(r[u].z) * a.G + sub, r[u].x >= 0 && lane_active);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (done) break;
-          if (r[u].x < 0) { done = true; break; }             // ran off the end of the kept points
-          if (r[u].y) {
-            if (!first) { done = true; break; }                // the next group's interval starts here
-            if (cur_cell >= 0 && lane_active) st_stream_f4(a.bev + (size_t)cur_cell * a.G + sub, acc);
-            acc = zero4;
-            cur_cell = r[u].x;
-          }
-          if (cur_cell >= 0) {
-            const float d = __int_as_float(r[u].w);
-            acc.x = fmaf(d, fj[u].x, acc.x);
-            acc.y = fmaf(d, fj[u].y, acc.y);
-            acc.z = fmaf(d, fj[u].z, acc.z);
-            acc.w = fmaf(d, fj[u].w, acc.w);
-          }
-        }
-        if (done) break;
+      const int n_valid = __popc(vbits);   // valid points are a prefix of the pass
+      int j_begin, j_end;
+      if (first) {        // own chunk: start at the first head, run to the end of the data in it
+        j_begin = hbits ? (__ffs(hbits) - 1) : n_valid;
+        j_end = n_valid;
+      } else {            // continuation: only the points before the first foreign head
+        j_begin = 0;
+        j_end = hbits ? (__ffs(hbits) - 1) : n_valid;
       }
-      if (done || cur_cell < 0) break;   // closed by a foreign head / end, or no interval started here
-      first = false;                     // keep following the open interval
+#pragma unroll 4
+      for (int j = j_begin; j < j_end; ++j) {
+        const int4 r = rec[j];
+        const float4 f = lane_active ? ldg_f4(src_lane + static_cast<uint32_t>(r.y)) : zero4;
+        if (first && ((hbits >> j) & 1u)) {      // a new interval starts: close the running one
+          if (cur_cell >= 0 && lane_active) st_stream_f4(bev_lane + static_cast<uint32_t>(cur_cell) * G, acc);
+          acc = zero4;
+          cur_cell = r.x;
+        }
+        const float d = __int_as_float(r.z);
+        acc.x = fmaf(d, f.x, acc.x);
+        acc.y = fmaf(d, f.y, acc.y);
+        acc.z = fmaf(d, f.z, acc.z);
+        acc.w = fmaf(d, f.w, acc.w);
+      }
+      // the open interval continues iff this pass was full and ended without meeting its end
+      if (cur_cell < 0 || j_end < width) break;
+      first = false;
       base += width;
       width = 4;
     }
-    if (cur_cell >= 0 && lane_active) st_stream_f4(a.bev + (size_t)cur_cell * a.G + sub, acc);
+    if (cur_cell >= 0 && lane_active) st_stream_f4(bev_lane + static_cast<uint32_t>(cur_cell) * G, acc);
   }
 }
 

@@ -29,12 +29,15 @@ dev = "cuda:0"
 cal = {k: torch.from_numpy(v).to(dev) for k, v in S.make_calibration(cfg).items()}
 us, vs, ds = (torch.from_numpy(a).to(dev) for a in O.frustum_axes(cfg.final_dim, cfg.downsample, cfg.dbound))
 grid = F.GridSpec.from_bounds(cfg.xbound, cfg.ybound, cfg.zbound)
+ft = {k: torch.from_numpy(v).to(dev) for k, v in S.make_features(cfg).items()}
 for _ in range(5):
     plan = F.build_plan(us, vs, ds, cal["rots"], cal["trans"], cal["intrins"], cal["post_rots"], cal["post_trans"], grid)
+    bev = F.lift_splat(ft["depth"], ft["feat"], plan)
 torch.cuda.synchronize()
 lib = _abi.load()
 lib.lss_debug_phase_ts.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
-for kernel, name, nblk in ((0, "partition_coop", (cfg.P + 1023) // 1024), (1, "local_sort", 1024)):
+for kernel, name, nblk in ((0, "partition_coop", (cfg.P + 1023) // 1024), (1, "local_sort", 1024),
+                           (2, "pool_fwd (0-1 FILL warp, 2-6 first REDUCE warp)", 148 * 8)):
     buf = np.zeros(4096 * 8, np.uint64)
     lib.lss_debug_phase_ts(kernel, buf.ctypes.data, buf.size)
     ts = buf.reshape(4096, 8)[:nblk].astype(np.int64)
