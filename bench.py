@@ -66,6 +66,12 @@ def cpu_port_run(cfg, steps, warmup, budget_s=None):
     cal = S.make_calibration(cfg); ft = S.make_features(cfg); dbev = S.make_dbev(cfg)
     us, vs, ds = O.frustum_axes(cfg.final_dim, cfg.downsample, cfg.dbound)
     dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    # all host threads the process may use (torchrun exports OMP_NUM_THREADS=1: override it)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    CO.set_threads(avail)
     cores = CO.threads()
 
     def one():
