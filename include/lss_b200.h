@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define LSS_ABI_VERSION 1
+#define LSS_ABI_VERSION 2
 
 typedef enum LssStatus {
   LSS_OK = 0,
@@ -144,16 +144,53 @@ int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid,
                   int32_t* d_counts, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * The plan: everything between the calibration tensors and the per-voxel point
+ * lists (K0 -> K1' -> sort -> intervals) in one call, i.e. the geometry half of
+ * get_voxels (src/model_baseline.py:128-131) + the argsort of :110 + the
+ * interval detection of src/tools.py:196-197.  The plan depends only on the
+ * calibration, so evaluation code can build it once per rig and reuse it.
+ *
+ * The sort key is the OUTPUT CELL ((b*X + x)*Y + y)*Z + z -- the reference's
+ * rank with its batch digit moved to the front, a bijection of the rank -- and
+ * the sort is stable, so each voxel's run holds the reference's points in the
+ * reference's order; runs follow one another sample-major instead of
+ * sample-minor.  (lss_sort_ranks is the bit-exact argsort of the rank itself.)
+ *   d_cells         (P)          output cell of every point, -1 if it fails the bounds test
+ *   d_cell_start    (n_cells+1)  cell c owns d_sorted_points[d_cell_start[c] .. d_cell_start[c+1]);
+ *                                equal bounds = empty voxel; d_cell_start[n_cells] = K.
+ *                                This table is the interval detection (K3).
+ *   d_sorted_points (P)          point ids ordered by (cell, point id); first K entries valid
+ *   d_sorted_cells  (P)          output cell of each sorted point; -1 beyond the K kept points
+ *   d_counts        (2)          {K kept points, V occupied voxels}
+ *   workspace: lss_plan_workspace_bytes(shape, grid) bytes, 16-byte aligned, ZERO-FILLED
+ *   before first use; a successful call leaves its control part zero again.
+ * lss_build_plan_from_geom is the same from a materialised geometry tensor d_geom
+ * (P,3) (the literal voxel_pooling(geom_feats, x) signature, src/model_baseline.py:84).
+ * ------------------------------------------------------------------------- */
+size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid);
+int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
+                   const float* d_trans, const float* d_intrins, const float* d_post_rots,
+                   const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
+                   int32_t* d_cells, int32_t* d_cell_start, int32_t* d_sorted_points,
+                   int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace, size_t workspace_bytes,
+                   void* stream);
+size_t lss_plan_from_geom_workspace_bytes(int64_t P, const LssGrid* grid, int32_t B);
+int lss_build_plan_from_geom(const float* d_geom, const LssGrid* grid, int32_t B, int64_t P,
+                             int32_t* d_cells, int32_t* d_cell_start, int32_t* d_sorted_points,
+                             int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * K4a dense pooling.  Replaces x[kept][sorts] -> QuickCumsum -> zeros ->
  *     index_put -> cat(unbind) (src/model_baseline.py:102-124) for a
- *     materialised frustum tensor d_x (P,C).  Every output element is written
- *     (zeros for empty voxels); d_bev is (B, C*Z, X, Y) in `layout`.  C <= 128.
+ *     materialised frustum tensor d_x (P,C), given a plan.  Every output element
+ *     is written (zeros for empty voxels); d_bev is (B, C*Z, X, Y) in `layout`.
+ *     C <= 128.
  *     Backward (QuickCumsum.backward src/tools.py:211-218 + index backward):
  *     d_dx[p,:] = d_dbev[cell(p),:] for kept points, 0 otherwise.
  * ------------------------------------------------------------------------- */
-int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points,
-                       const int32_t* d_sorted_cells, const int32_t* d_cell_range,
-                       const int32_t* d_counts, const LssGrid* grid, int32_t B, int32_t C,
+int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
+                       const int32_t* d_cell_start, const LssGrid* grid, int32_t B, int32_t C, int64_t P,
                        int32_t layout, float* d_bev, void* stream);
 int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGrid* grid,
                        int32_t B, int32_t C, int64_t P, int32_t layout, float* d_dx,
@@ -174,37 +211,17 @@ int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* sh
  * K4  fused lift + splat forward.  bev[cell, c] = sum over the cell's points of
  *     depth[pixel, d] * feat[pixel, c]; the frustum tensor never exists.
  *     Replaces src/modules.py:84 + src/model_baseline.py:79-80,89,102-124 +
- *     src/tools.py:194-208.  Inputs are the staged d_depth_t / d_feat_t.
+ *     src/tools.py:194-208.  Inputs are the staged d_depth_t / d_feat_t and a plan.
  * K5  fused backward.  d_ddepth (BN,D,fH,fW) = sum_c g*feat, d_dfeat
  *     (BN,C,fH,fW) = sum_d g*depth with g = dbev[cell(point), :] (an exact
  *     gather, as QuickCumsum.backward is); points that were dropped contribute 0.
  * ------------------------------------------------------------------------- */
-int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t,
-                      const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
-                      const int32_t* d_cell_range, const int32_t* d_counts, const LssGrid* grid,
+int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32_t* d_sorted_points,
+                      const int32_t* d_sorted_cells, const int32_t* d_cell_start, const LssGrid* grid,
                       const LssShape* shape, int32_t layout, float* d_bev, void* stream);
 int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
                       const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
                       int32_t layout, float* d_ddepth, float* d_dfeat, void* stream);
-
-/* ------------------------------------------------------------------------- *
- * One-shot plan: everything between the calibration tensors and the sorted /
- * interval tables (K0 -> K1' -> K2 -> K3) in one call, i.e. the geometry half
- * of get_voxels (src/model_baseline.py:128-133).  The plan depends only on the
- * calibration, so evaluation code can build it once per rig and reuse it.
- *   workspace: lss_plan_workspace_bytes(shape, grid) bytes, zero-filled before
- *   first use (a successful call leaves the reusable part zero again);
- *   outputs: d_cells (P), d_sorted_points (P) and d_sorted_cells (P) (first K entries
- *   valid, the order of the dropped points behind them is unspecified),
- *   d_cell_range (n_cells,2), d_counts (2); all fully written by the call itself.
- * ------------------------------------------------------------------------- */
-size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid);
-int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
-                   const float* d_trans, const float* d_intrins, const float* d_post_rots,
-                   const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
-                   int32_t* d_cells, int32_t* d_sorted_points, int32_t* d_sorted_cells,
-                   int32_t* d_cell_range, int32_t* d_counts, void* d_workspace,
-                   size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "liblss_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
+ABI_VERSION = 2
 LSS_BEV_NHWC = 0
 LSS_BEV_NCHW = 1
 
@@ -50,13 +51,15 @@ SIGNATURES = {
     "lss_sort_workspace_bytes": (_sz, [_i64, _i32]),
     "lss_sort_ranks": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
     "lss_intervals": (C.c_int, [_p, _i64, _G, _i32, _p, _p, _p, _p, _p]),
-    "lss_pool_dense_fwd": (C.c_int, [_p, _p, _p, _p, _p, _G, _i32, _i32, _i32, _p, _p]),
+    "lss_pool_dense_fwd": (C.c_int, [_p, _p, _p, _p, _G, _i32, _i32, _i64, _i32, _p, _p]),
     "lss_pool_dense_bwd": (C.c_int, [_p, _p, _G, _i32, _i32, _i64, _i32, _p, _p]),
     "lss_lift_stage": (C.c_int, [_p, _p, _S, _p, _p, _p]),
-    "lss_liftsplat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _G, _S, _i32, _p, _p]),
+    "lss_liftsplat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _G, _S, _i32, _p, _p]),
     "lss_liftsplat_bwd": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _p, _p, _p]),
     "lss_plan_workspace_bytes": (_sz, [_S, _G]),
     "lss_build_plan": (C.c_int, [_p] * 8 + [_G, _S, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "lss_plan_from_geom_workspace_bytes": (_sz, [_i64, _G, _i32]),
+    "lss_build_plan_from_geom": (C.c_int, [_p, _G, _i32, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lock = threading.Lock()
@@ -81,8 +84,8 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.lss_abi_version() != 1:
-            raise RuntimeError("liblss_b200.so ABI version %d, expected 1" % lib.lss_abi_version())
+        if lib.lss_abi_version() != ABI_VERSION:
+            raise RuntimeError("liblss_b200.so ABI version %d, expected %d" % (lib.lss_abi_version(), ABI_VERSION))
         _lib = lib
     return _lib
 

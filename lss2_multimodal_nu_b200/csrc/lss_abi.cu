@@ -6,7 +6,7 @@
 #include "lss_pool.cuh"
 #include "lss_sort.cuh"
 #include "lss_sort_small.cuh"
-#include "lss_partition.cuh"
+#include "lss_plan.cuh"
 
 namespace lss {
 char* cuda_error_buffer() {
@@ -64,104 +64,73 @@ static int launch_intervals(const int32_t* sorted_ranks, long long P, const Grid
   return LSS_OK;
 }
 
-// ---- co-resident partition path (lss_partition.cuh) -------------------------------------
-struct CoopPlan {
-  bool ok;
-  int tiles, hi_bits, lo_bits, n_buckets;
-  size_t off_keys, off_vals, off_rows, off_excl, off_totals, off_bucket_start, off_barrier, total_bytes;
-};
-
-static int coop_capacity() {
-  static int cached[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (cached[dev] == 0) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_coop_kernel, kPartThreads, 0) != cudaSuccess)
-      per_sm = 0;
-    cached[dev] = per_sm * sm_count() + 1;  // +1: 0 means "not queried"
-  }
-  return cached[dev] - 1;
-}
-
-static CoopPlan make_coop_plan(long long P, int32_t n_cells, int ppc, bool query_device) {
-  CoopPlan c;
-  memset(&c, 0, sizeof(c));
-  int kb = 0;
-  while ((1ll << kb) <= (long long)n_cells) ++kb;
-  if (kb < 2) kb = 2;
-  c.hi_bits = kb - 1 < kPartMaxBits ? kb - 1 : kPartMaxBits;
-  c.lo_bits = kb - c.hi_bits;
-  c.n_buckets = 1 << c.hi_bits;
-  const long long tiles = (P + kPartTile - 1) / kPartTile;
-  c.tiles = (int)tiles;
-  c.ok = c.lo_bits <= kLocalMaxBits && tiles <= kPartMaxTiles && ppc > 0 &&
-         (kPartTile - 1) / ppc + 2 <= kPartMaxCams;
-  if (c.ok && query_device) c.ok = tiles <= coop_capacity();
-  size_t off = 0;
-  c.off_keys = off; off += align_up((size_t)P * 4, 256);
-  c.off_vals = off; off += align_up((size_t)P * 4, 256);
-  c.off_rows = off; off += align_up((size_t)tiles * kPartMaxBins * 2, 256);
-  c.off_excl = off; off += align_up((size_t)tiles * kPartMaxBins * 4, 256);
-  c.off_totals = off; off += align_up((size_t)kPartMaxBins * 4, 256);
-  c.off_bucket_start = off; off += align_up((size_t)(kPartMaxBins + 1) * 4, 256);
-  c.off_barrier = off; off += 256;
-  c.total_bytes = off;
-  return c;
-}
-
-static int run_coop_plan(const CoopPlan& c, const GeomArgs& ga, const GridDev& g, long long P,
-                         int32_t* d_cells, int32_t* sorted_points, int32_t* sorted_cells,
-                         int32_t* cell_range, int32_t* counts, void* ws, cudaStream_t st) {
+// ---- the plan: P1 cells -> P2 scan -> P3 scatter -> P4 order (lss_plan.cuh) ---------------
+static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& g, long long P,
+                    long long points_per_sample, int32_t* d_cells, int32_t* d_cell_start,
+                    int32_t* d_sorted_points, int32_t* d_sorted_cells, int32_t* d_counts, void* ws,
+                    size_t ws_bytes, cudaStream_t st) {
+  const PlanWorkspace pw = make_plan_workspace(P, g.n_cells);
+  LSS_REQUIRE(ws_bytes >= pw.total_bytes, LSS_ERR_WORKSPACE_TOO_SMALL);
+  LSS_REQUIRE(aligned16(ws) && aligned16(d_cell_start), LSS_ERR_MISALIGNED);
   char* w = static_cast<char*>(ws);
-  PartitionArgs a;
-  memset(&a, 0, sizeof(a));
-  a.geom = ga; a.grid = g;
-  const int hw = ga.fH * ga.fW;
-  a.div_ppc = FastDiv((uint32_t)(ga.D * hw)); a.div_hw = FastDiv((uint32_t)hw);
-  a.div_w = FastDiv((uint32_t)ga.fW); a.div_n = FastDiv((uint32_t)ga.N);
-  a.P = P; a.tiles = c.tiles; a.shift = c.lo_bits; a.bits = c.hi_bits;
-  a.cells = d_cells;
-  a.part_keys = reinterpret_cast<int32_t*>(w + c.off_keys);
-  a.part_vals = reinterpret_cast<int32_t*>(w + c.off_vals);
-  a.rows = reinterpret_cast<uint16_t*>(w + c.off_rows);
-  a.excl = reinterpret_cast<uint32_t*>(w + c.off_excl);
-  a.totals = reinterpret_cast<uint32_t*>(w + c.off_totals);
-  a.bucket_start = reinterpret_cast<uint32_t*>(w + c.off_bucket_start);
-  a.counts = counts;
-  a.barrier = reinterpret_cast<uint32_t*>(w + c.off_barrier);
-  partition_coop_kernel<<<c.tiles, kPartThreads, 0, st>>>(a);
-  LSS_LAUNCH_CHECK("partition_coop_kernel");
-  LocalArgs l;
-  memset(&l, 0, sizeof(l));
-  l.keys = a.part_keys; l.vals = a.part_vals; l.bucket_start = a.bucket_start;
-  l.sorted_points = sorted_points; l.sorted_ranks = nullptr; l.sorted_cells = sorted_cells;
-  l.cell_range = reinterpret_cast<int2*>(cell_range); l.counts = counts;
-  l.g = g;
-  l.div_b = FastDiv(g.B); l.div_z = FastDiv(g.nx[2]); l.div_y = FastDiv(g.nx[1]);
-  l.lo_bits = c.lo_bits;
-  return launch_local_sort(l, c.n_buckets, st);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(w + pw.off_cnt);
+  uint32_t* state = reinterpret_cast<uint32_t*>(w + pw.off_state);
+  uint32_t* ctl = reinterpret_cast<uint32_t*>(w + pw.off_ctl);
+  int32_t* tmp_pt = reinterpret_cast<int32_t*>(w + pw.off_tmp_pt);
+  int32_t* long_list = reinterpret_cast<int32_t*>(w + pw.off_long);
+
+  PlanCellsArgs ca;
+  memset(&ca, 0, sizeof(ca));
+  ca.grid = g; ca.P = P; ca.cells = d_cells; ca.cnt = cnt; ca.counts = d_counts; ca.ctl = ctl;
+  const unsigned tiles = (unsigned)((P + kPlanTile - 1) / kPlanTile);
+  if (ga) {
+    ca.geom = *ga;
+    const int hw = ga->fH * ga->fW;
+    LSS_REQUIRE((kPlanTile - 1) / (ga->D * hw) + 2 <= kPlanMaxCams, LSS_ERR_UNSUPPORTED);
+    ca.div_ppc = FastDiv((uint32_t)(ga->D * hw)); ca.div_hw = FastDiv((uint32_t)hw);
+    ca.div_w = FastDiv((uint32_t)ga->fW); ca.div_n = FastDiv((uint32_t)ga->N);
+    plan_cells_kernel<false><<<tiles, kPlanThreads, 0, st>>>(ca);
+  } else {
+    ca.dense_geom = dense_geom;
+    ca.div_pps = FastDiv((uint32_t)points_per_sample);
+    plan_cells_kernel<true><<<tiles, kPlanThreads, 0, st>>>(ca);
+  }
+  LSS_LAUNCH_CHECK("plan_cells_kernel");
+
+  PlanScanArgs sa;
+  sa.cnt = cnt; sa.n = g.n_cells; sa.tiles = pw.scan_tiles; sa.cell_start = d_cell_start;
+  sa.state = state; sa.ctl = ctl; sa.counts = d_counts; sa.long_list = long_list;
+  plan_scan_kernel<<<(unsigned)pw.scan_tiles, kPlanThreads, 0, st>>>(sa);
+  LSS_LAUNCH_CHECK("plan_scan_kernel");
+
+  PlanScatterArgs sc;
+  sc.cells = d_cells; sc.P = P; sc.cnt = cnt; sc.cell_start = d_cell_start;
+  sc.tmp_pt = tmp_pt; sc.sorted_cells = d_sorted_cells; sc.state = state; sc.scan_tiles = pw.scan_tiles; sc.ctl = ctl;
+  long long blocks = (P + kPlanThreads - 1) / kPlanThreads;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  plan_scatter_kernel<<<(unsigned)blocks, kPlanThreads, 0, st>>>(sc);
+  LSS_LAUNCH_CHECK("plan_scatter_kernel");
+
+  PlanOrderArgs oa;
+  oa.tmp_pt = tmp_pt; oa.sorted_cells = d_sorted_cells; oa.cell_start = d_cell_start; oa.n_cells = g.n_cells;
+  oa.P = P; oa.sorted_points = d_sorted_points; oa.ctl = ctl; oa.long_list = long_list;
+  plan_order_kernel<<<(unsigned)blocks, kPlanThreads, 0, st>>>(oa);
+  LSS_LAUNCH_CHECK("plan_order_kernel");
+  return LSS_OK;
 }
 
 template <int kLanes>
-static int launch_bwd(const PoolBwdArgs& a, int blocks, size_t smem, cudaStream_t st) {
-  if (smem > 48 * 1024) {
-    LSS_CUDA_TRY(cudaFuncSetAttribute(liftsplat_bwd_nhwc_kernel<kLanes>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "cudaFuncSetAttribute(bwd smem)");
-  }
-  liftsplat_bwd_nhwc_kernel<kLanes><<<blocks, 256, smem, st>>>(a);
+static int launch_bwd(const PoolBwdArgs& a, int blocks, cudaStream_t st) {
+  liftsplat_bwd_nhwc_kernel<kLanes><<<blocks, kBwdThreads, 0, st>>>(a);
   LSS_LAUNCH_CHECK("liftsplat_bwd_nhwc_kernel");
   return LSS_OK;
 }
 template <bool kFused>
 static int launch_pool_fwd(const PoolFwdArgs& a, int blocks, cudaStream_t st) {
-  const int G = a.G;
-  if (G <= 4) pool_fwd_nhwc_kernel<kFused, 4><<<blocks, kPoolThreads, 0, st>>>(a);
-  else if (G <= 8) pool_fwd_nhwc_kernel<kFused, 8><<<blocks, kPoolThreads, 0, st>>>(a);
-  else if (G <= 16) pool_fwd_nhwc_kernel<kFused, 16><<<blocks, kPoolThreads, 0, st>>>(a);
-  else pool_fwd_nhwc_kernel<kFused, 32><<<blocks, kPoolThreads, 0, st>>>(a);
+  if (a.C <= 32) pool_fwd_nhwc_kernel<kFused, 1><<<blocks, kPoolThreads, 0, st>>>(a);
+  else if (a.C <= 64 && a.C % 2 == 0) pool_fwd_nhwc_kernel<kFused, 2><<<blocks, kPoolThreads, 0, st>>>(a);
+  else pool_fwd_nhwc_kernel<kFused, 4><<<blocks, kPoolThreads, 0, st>>>(a);
   LSS_LAUNCH_CHECK("pool_fwd_nhwc_kernel");
   return LSS_OK;
 }
@@ -283,12 +252,11 @@ int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid,
 }
 
 static int pool_fwd_common(bool fused, const float* d_depth_t, const float* d_feat_t,
-                           const float* d_x, const int32_t* d_sorted_points,
-                           const int32_t* d_sorted_cells, const int32_t* d_cell_range,
-                           const int32_t* d_counts, const LssGrid* grid, int32_t B, int32_t C,
-                           int32_t D, int32_t HW, long long dhw, int32_t layout, float* d_bev,
+                           const float* d_x, const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
+                           const int32_t* d_cell_start, const LssGrid* grid, int32_t B, int32_t C,
+                           int32_t D, int32_t HW, long long dhw, long long P, int32_t layout, float* d_bev,
                            cudaStream_t st) {
-  LSS_REQUIRE(d_sorted_points && d_sorted_cells && d_cell_range && d_counts && d_bev, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(d_sorted_points && d_sorted_cells && d_cell_start && d_bev, LSS_ERR_NULL_POINTER);
   GridDev g;
   int rc = make_grid(grid, B, &g);
   if (rc) return rc;
@@ -296,37 +264,36 @@ static int pool_fwd_common(bool fused, const float* d_depth_t, const float* d_fe
   LSS_REQUIRE(C <= 128, LSS_ERR_UNSUPPORTED);
   LSS_REQUIRE(aligned16(d_bev), LSS_ERR_MISALIGNED);
   LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
+  LSS_REQUIRE(P > 0 && P < (1ll << 30), LSS_ERR_BAD_DIMENSION);
   PoolFwdArgs a;
   memset(&a, 0, sizeof(a));
-  a.depth_t = d_depth_t; a.feat_t = reinterpret_cast<const float4*>(d_feat_t);
-  a.x = reinterpret_cast<const float4*>(d_x);
-  a.sorted_points = d_sorted_points; a.sorted_cells = d_sorted_cells; a.counts = d_counts;
-  a.cell_range = reinterpret_cast<const int2*>(d_cell_range);
-  a.bev = reinterpret_cast<float4*>(d_bev);
-  a.n_cells = (uint32_t)g.n_cells;
-  a.G = C / 4; a.D = D; a.HW = HW;
-  LSS_REQUIRE((long long)g.n_cells * a.G < (1ll << 31), LSS_ERR_BAD_DIMENSION);
-  a.fill_warps = 1;
-  int blocks_per_sm = 12;
-  if (const char* e = getenv("LSS_FILL_WARPS")) a.fill_warps = atoi(e);          // tuning knobs
-  if (const char* e = getenv("LSS_POOL_BLOCKS_PER_SM")) blocks_per_sm = atoi(e);
-  if (a.fill_warps < 1) a.fill_warps = 1;
-  if (a.fill_warps > kPoolWarps - 1) a.fill_warps = kPoolWarps - 1;
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
-  a.div_g = FastDiv(a.G);
+  a.depth_t = d_depth_t; a.feat_t = d_feat_t; a.x = d_x;
+  a.sorted_points = d_sorted_points; a.sorted_cells = d_sorted_cells; a.cell_start = d_cell_start;
+  a.bev = d_bev; a.P = P; a.n_cells = g.n_cells;
+  a.C = C; a.D = D; a.HW = HW;
   a.div_dhw = FastDiv((uint32_t)(dhw > 0 ? dhw : 1)); a.div_hw = FastDiv((uint32_t)(HW > 0 ? HW : 1));
-  const int blocks = sm_count() * blocks_per_sm;
-  return fused ? launch_pool_fwd<true>(a, blocks, st) : launch_pool_fwd<false>(a, blocks, st);
+  a.div_g4 = FastDiv((uint32_t)(C / 4));
+  // fill CTAs: one per SM by default, so the zero stream runs in the background for the whole kernel
+  long long fill = sm_count();
+  const long long fill_blocks = ((long long)g.n_cells + 31) / 32;
+  if (fill * kPoolWarps > fill_blocks) fill = (fill_blocks + kPoolWarps - 1) / kPoolWarps;
+  if (const char* e = getenv("LSS_FILL_CTAS")) fill = atoi(e);   // tuning knob
+  if (fill < 1) fill = 1;
+  a.fill_ctas = (int)fill;
+  const long long reduce = (P + (long long)kPoolChunk * kPoolWarps - 1) / ((long long)kPoolChunk * kPoolWarps);
+  const long long blocks = fill + reduce;
+  LSS_REQUIRE(blocks < (1ll << 31), LSS_ERR_BAD_DIMENSION);
+  return fused ? launch_pool_fwd<true>(a, (int)blocks, st) : launch_pool_fwd<false>(a, (int)blocks, st);
 }
 
-int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points,
-                       const int32_t* d_sorted_cells, const int32_t* d_cell_range,
-                       const int32_t* d_counts, const LssGrid* grid, int32_t B, int32_t C,
+int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
+                       const int32_t* d_cell_start, const LssGrid* grid, int32_t B, int32_t C, int64_t P,
                        int32_t layout, float* d_bev, void* stream) {
   LSS_REQUIRE(d_x, LSS_ERR_NULL_POINTER);
   LSS_REQUIRE(aligned16(d_x), LSS_ERR_MISALIGNED);
-  return pool_fwd_common(false, nullptr, nullptr, d_x, d_sorted_points, d_sorted_cells, d_cell_range,
-                         d_counts, grid, B, C, 1, 1, 1, layout, d_bev, as_stream(stream));
+  LSS_REQUIRE((long long)P * (C / 4) < (1ll << 32), LSS_ERR_BAD_DIMENSION);   // 16-byte row offsets in 32 bits
+  return pool_fwd_common(false, nullptr, nullptr, d_x, d_sorted_points, d_sorted_cells, d_cell_start, grid, B,
+                         C, 1, 1, 1, P, layout, d_bev, as_stream(stream));
 }
 
 int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGrid* grid,
@@ -366,18 +333,17 @@ int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* sh
   return LSS_OK;
 }
 
-int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t,
-                      const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
-                      const int32_t* d_cell_range, const int32_t* d_counts, const LssGrid* grid,
+int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32_t* d_sorted_points,
+                      const int32_t* d_sorted_cells, const int32_t* d_cell_start, const LssGrid* grid,
                       const LssShape* shape, int32_t layout, float* d_bev, void* stream) {
   LSS_REQUIRE(d_depth_t && d_feat_t, LSS_ERR_NULL_POINTER);
   int rc = check_shape(shape);
   if (rc) return rc;
   LSS_REQUIRE(aligned16(d_feat_t), LSS_ERR_MISALIGNED);
   const int HW = shape->fH * shape->fW;
-  return pool_fwd_common(true, d_depth_t, d_feat_t, nullptr, d_sorted_points, d_sorted_cells,
-                         d_cell_range, d_counts, grid, shape->B, shape->C, shape->D, HW,
-                         (long long)shape->D * HW, layout, d_bev, as_stream(stream));
+  return pool_fwd_common(true, d_depth_t, d_feat_t, nullptr, d_sorted_points, d_sorted_cells, d_cell_start,
+                         grid, shape->B, shape->C, shape->D, HW, (long long)shape->D * HW, shape_points(shape),
+                         layout, d_bev, as_stream(stream));
 }
 
 int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
@@ -396,18 +362,16 @@ int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* 
   a.feat_t = reinterpret_cast<const float4*>(d_feat_t); a.cells = d_cells;
   a.ddepth = d_ddepth; a.dfeat = d_dfeat;
   a.D = shape->D; a.fH = shape->fH; a.fW = shape->fW; a.C = shape->C; a.G = shape->C / 4;
+  a.n_pix = shape->B * shape->N * shape->fH * shape->fW;
+  a.div_fh = FastDiv((uint32_t)shape->fH); a.div_fw = FastDiv((uint32_t)shape->fW);
+  LSS_REQUIRE((long long)g.n_cells * a.G < (1ll << 31), LSS_ERR_BAD_DIMENSION);
   const int G = a.G;
-  const int lanes = G <= 4 ? 4 : G <= 8 ? 8 : G <= 16 ? 16 : 32;
-  const int round = (32 / lanes) * (lanes >= 8 ? 8 : lanes);   // depth bins per kernel round
-  const int Dpad = (a.D + round - 1) / round * round;
-  const size_t smem = ((size_t)3 * Dpad * a.fW + (size_t)a.C * (a.fW + 1)) * 4;
-  LSS_REQUIRE(smem <= 200 * 1024, LSS_ERR_UNSUPPORTED);
-  const int blocks = shape->B * shape->N * shape->fH;
+  const int blocks = (a.n_pix + kBwdWarps - 1) / kBwdWarps;
   cudaStream_t st = as_stream(stream);
-  if (G <= 4) return launch_bwd<4>(a, blocks, smem, st);
-  if (G <= 8) return launch_bwd<8>(a, blocks, smem, st);
-  if (G <= 16) return launch_bwd<16>(a, blocks, smem, st);
-  if (G <= 32) return launch_bwd<32>(a, blocks, smem, st);
+  if (G <= 4) return launch_bwd<4>(a, blocks, st);
+  if (G <= 8) return launch_bwd<8>(a, blocks, st);
+  if (G <= 16) return launch_bwd<16>(a, blocks, st);
+  if (G <= 32) return launch_bwd<32>(a, blocks, st);
   return LSS_ERR_UNSUPPORTED;
 }
 
@@ -415,81 +379,57 @@ size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid) {
   if (check_shape(shape) != LSS_OK) return 0;
   GridDev g;
   if (make_grid(grid, shape->B, &g) != LSS_OK) return 0;
-  const long long P = shape_points(shape);
-  const SortPlan s = make_sort_plan(P, g.n_cells);
-  const size_t general = make_msd_plan(s).total_bytes + 2 * align_up((size_t)P * 4, 256);
-  const size_t coop = make_coop_plan(P, g.n_cells, shape->D * shape->fH * shape->fW, false).total_bytes;
-  return general > coop ? general : coop;
+  return make_plan_workspace(shape_points(shape), g.n_cells).total_bytes;
 }
 
 int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
                    const float* d_trans, const float* d_intrins, const float* d_post_rots,
                    const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
-                   int32_t* d_cells, int32_t* d_sorted_points, int32_t* d_sorted_cells,
-                   int32_t* d_cell_range, int32_t* d_counts, void* d_workspace,
-                   size_t workspace_bytes, void* stream) {
-  LSS_REQUIRE(d_us && d_vs && d_ds && d_rots && d_trans && d_intrins && d_post_rots &&
-                  d_post_trans && d_cells && d_sorted_points && d_sorted_cells && d_cell_range && d_counts &&
-                  d_workspace, LSS_ERR_NULL_POINTER);
+                   int32_t* d_cells, int32_t* d_cell_start, int32_t* d_sorted_points,
+                   int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace, size_t workspace_bytes,
+                   void* stream) {
+  LSS_REQUIRE(d_us && d_vs && d_ds && d_rots && d_trans && d_intrins && d_post_rots && d_post_trans &&
+                  d_cells && d_cell_start && d_sorted_points && d_sorted_cells && d_counts && d_workspace,
+              LSS_ERR_NULL_POINTER);
   int rc = check_shape(shape);
   if (rc) return rc;
   GridDev g;
   rc = make_grid(grid, shape->B, &g);
   if (rc) return rc;
-  LSS_REQUIRE(aligned16(d_workspace), LSS_ERR_MISALIGNED);
-  const long long P = shape_points(shape);
-  const SortPlan s = make_sort_plan(P, g.n_cells);
-  const size_t ws_sort = make_msd_plan(s).total_bytes;
-  const CoopPlan coop = make_coop_plan(P, g.n_cells, shape->D * shape->fH * shape->fW, true);
-  size_t need = ws_sort + 2 * align_up((size_t)P * 4, 256);
-  if (coop.total_bytes > need) need = coop.total_bytes;
-  LSS_REQUIRE(workspace_bytes >= need, LSS_ERR_WORKSPACE_TOO_SMALL);
-  cudaStream_t st = as_stream(stream);
-  char* w = static_cast<char*>(d_workspace);
-  int32_t* ranks = reinterpret_cast<int32_t*>(w + ws_sort);
-  int32_t* sorted_ranks = reinterpret_cast<int32_t*>(w + ws_sort + align_up((size_t)P * 4, 256));
-
   GeomArgs ga;
   memset(&ga, 0, sizeof(ga));
   ga.us = d_us; ga.vs = d_vs; ga.ds = d_ds;
   ga.post_trans = d_post_trans; ga.trans = d_trans;
   ga.rots = d_rots; ga.intrins = d_intrins; ga.post_rots = d_post_rots;
   ga.raw = 1; ga.N = shape->N; ga.D = shape->D; ga.fH = shape->fH; ga.fW = shape->fW;
-  const int ppc = shape->D * shape->fH * shape->fW;
-  if (coop.ok)  // all tiles co-resident: K0 + K1' + partition in one kernel, then local sort + intervals
-    return run_coop_plan(coop, ga, g, P, d_cells, d_sorted_points, d_sorted_cells, d_cell_range, d_counts,
-                         d_workspace, st);
-  const MsdPlan msd = make_msd_plan(s);
-  if (msd.ok && (kSortTile - 1) / ppc + 2 <= kSmallMaxCams) {
-    // single wave: P1 = K0 + K1' + MSD partition, P2 = local sort + intervals (K2 + K3)
-    SmallGeom sg;
-    sg.enabled = true; sg.geom = ga; sg.grid = g; sg.cells = d_cells;
-    return run_msd_plan(s, msd, sg, d_sorted_points, d_sorted_cells, d_cell_range, d_counts, P, d_workspace, st);
-  }
-  LSS_CUDA_TRY(cudaMemsetAsync(d_cell_range, 0, (size_t)g.n_cells * 8, st), "memset cell_range");
-  LSS_CUDA_TRY(cudaMemsetAsync(d_counts, 0, 8, st), "memset counts");
-  PointOut out{nullptr, nullptr, ranks, d_cells};
-  if (s.small) {
-    rc = launch_geometry(ga, g, shape, out, nullptr, st);
-    if (rc) return rc;
-    rc = run_sort_passes_small(s, ranks, sorted_ranks, d_sorted_points, P, d_workspace, nullptr, st);
-    if (rc) return rc;
-    return launch_intervals(sorted_ranks, P, g, nullptr, d_sorted_cells, d_cell_range, d_counts, nullptr, 0, st);
-  }
-  SortDigits sd = sort_digits(s, d_workspace);
-  rc = launch_geometry(ga, g, shape, out, &sd, st);
+  const long long P = shape_points(shape);
+  return run_plan(&ga, nullptr, g, P, P / shape->B, d_cells, d_cell_start, d_sorted_points, d_sorted_cells,
+                  d_counts, d_workspace, workspace_bytes, as_stream(stream));
+}
+
+int lss_build_plan_from_geom(const float* d_geom, const LssGrid* grid, int32_t B, int64_t P,
+                             int32_t* d_cells, int32_t* d_cell_start, int32_t* d_sorted_points,
+                             int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace,
+                             size_t workspace_bytes, void* stream) {
+  LSS_REQUIRE(d_geom && d_cells && d_cell_start && d_sorted_points && d_sorted_cells && d_counts && d_workspace,
+              LSS_ERR_NULL_POINTER);
+  GridDev g;
+  int rc = make_grid(grid, B, &g);
   if (rc) return rc;
-  rc = run_sort_passes(s, ranks, sorted_ranks, d_sorted_points, P, d_workspace, st);
-  if (rc) return rc;
-  // K3 also wipes the sort's control words so the workspace is ready for the next call
-  return launch_intervals(sorted_ranks, P, g, nullptr, d_sorted_cells, d_cell_range, d_counts,
-                          reinterpret_cast<uint32_t*>(w + s.off_control),
-                          (long long)(s.control_bytes / 4), st);
+  LSS_REQUIRE(P > 0 && P < (1ll << 30) && P % B == 0, LSS_ERR_BAD_DIMENSION);
+  return run_plan(nullptr, d_geom, g, P, P / B, d_cells, d_cell_start, d_sorted_points, d_sorted_cells,
+                  d_counts, d_workspace, workspace_bytes, as_stream(stream));
+}
+
+size_t lss_plan_from_geom_workspace_bytes(int64_t P, const LssGrid* grid, int32_t B) {
+  GridDev g;
+  if (P <= 0 || P >= (1ll << 30) || make_grid(grid, B, &g) != LSS_OK) return 0;
+  return make_plan_workspace(P, g.n_cells).total_bytes;
 }
 
 #ifdef LSS_PHASE_TIMING
 int lss_debug_phase_ts(int kernel, unsigned long long* host_out, int n) {
-  return (int)cudaMemcpyFromSymbol(host_out, g_phase_ts, (size_t)n * 8, (size_t)kernel * 4096 * 8 * 8);
+  return (int)cudaMemcpyFromSymbol(host_out, g_phase_ts, (size_t)n * 8, (size_t)kernel * 4096 * 16 * 8);
 }
 #endif
 

@@ -111,19 +111,19 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // Optional phase timestamps (build with -DLSS_PHASE_TIMING; tools/phase_timing.py reads them).
 #ifdef LSS_PHASE_TIMING
-__device__ unsigned long long g_phase_ts[3][4096 * 8];
+__device__ unsigned long long g_phase_ts[3][4096 * 16];
 __device__ __forceinline__ void phase_stamp_any(int kernel, int slot) {   // caller picks the thread
   if (blockIdx.x < 4096) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_phase_ts[kernel][blockIdx.x * 8 + slot] = t;
+    g_phase_ts[kernel][blockIdx.x * 16 + slot] = t;
   }
 }
 __device__ __forceinline__ void phase_stamp(int kernel, int slot) {
   if (threadIdx.x == 0 && blockIdx.x < 4096) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_phase_ts[kernel][blockIdx.x * 8 + slot] = t;
+    g_phase_ts[kernel][blockIdx.x * 16 + slot] = t;
   }
 }
 #else

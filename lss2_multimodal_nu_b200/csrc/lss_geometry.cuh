@@ -150,7 +150,7 @@ struct SortDigits {
 
 __device__ __forceinline__ int32_t quantize_point_core(float gx, float gy, float gz, int b,
                                                        const GridDev& g, long long p,
-                                                       const PointOut& out) {
+                                                       const PointOut& out, int32_t* cell_ret = nullptr) {
   // ((geom - (bx - dx/2)) / dx).long()   reference src/model_baseline.py:92
   const float qx = __fdiv_rn(__fsub_rn(gx, g.off[0]), g.dx[0]);
   const float qy = __fdiv_rn(__fsub_rn(gy, g.off[1]), g.dx[1]);
@@ -174,6 +174,7 @@ __device__ __forceinline__ int32_t quantize_point_core(float gx, float gy, float
   }
   if (out.ranks) out.ranks[p] = rank;
   if (out.cells) out.cells[p] = cell;
+  if (cell_ret) *cell_ret = cell;
   return rank;
 }
 

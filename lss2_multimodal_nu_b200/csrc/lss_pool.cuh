@@ -109,166 +109,245 @@ lift_stage_kernel(const float* __restrict__ depth, const float* __restrict__ fea
 // --------------------------------------------------------------------------
 // K4 / K4a forward, channels-innermost BEV.
 //
-// The BEV map is addressed as (cell, G) float4 vectors, cell = ((b*X + x)*Y + y)*Z + z
-// and G = C/4, so one voxel is one contiguous line.  Every output element is
-// written exactly once (this replaces torch.zeros + index_put + cat of
-// reference src/model_baseline.py:120-124) by two kinds of warps that run side
-// by side in every CTA:
-//   * FILL warps stream zeros into the empty voxels (about 75 % of the map at
-//     the headline config), one contiguous 512-byte line per warp store;
-//   * REDUCE warps do the warp-level segmented reduction over the sorted point
-//     list: kLanes lanes (a power of two >= G) own one voxel interval at a time,
-//     each lane one float4 of channels.  A group loads kLanes consecutive sorted
-//     points cooperatively (point id, output cell, depth), broadcasts them with
-//     shuffles and walks them in order: a change of cell closes the running sum
-//     (one 16*G-byte store) and opens the next.  A group owns the intervals that
-//     START inside its chunk and follows the last one past the chunk end.
-// The walk order is the sort order, so per-voxel sums are bit-reproducible.
-//   kFused:  acc += depth_t[pixel*D + d] * feat_t[pixel, :]   (K4: the frustum
-//            tensor of src/modules.py:84 is never formed)
-//   !kFused: acc += x[point, :]                                (K4a)
+// The BEV map is (cell, C) with cell = ((b*X + x)*Y + y)*Z + z, one voxel = one
+// contiguous line, and the plan's point list is sorted by cell, so cell c owns
+// sorted_points[cell_start[c] .. cell_start[c+1]).  Every output element is
+// written exactly once (this is the torch.zeros + index_put + cat of reference
+// src/model_baseline.py:120-124) by two kinds of CTAs that run side by side:
+//   * FILL CTAs stream zeros into the empty voxels (75 % of the map at the
+//     headline config): a warp reads the 33 interval bounds of 32 consecutive
+//     cells with one coalesced load (the next block's are prefetched) and covers
+//     the empty lines with 128-bit stores;
+//   * REDUCE CTAs do the warp-level segmented reduction over the sorted point
+//     list.  A warp takes 32 consecutive sorted points -- the unit of work is the
+//     POINT, so dense and sparse regions of the map cost the same -- and owns
+//     the intervals that START among them; the last one is followed into the
+//     next chunk.  One coalesced load brings point ids and cells, the lanes
+//     decode them, gather the depths and stage {feature-row offset, depth, cell}
+//     in shared memory; then the warp walks the records in order with
+//     (kS - 1) * kU feature-row gathers in flight (software pipeline), every lane
+//     owning kVec channels (C = 64: 32 lanes x 8 bytes = one 256-byte row per
+//     load), closing the running sum at every interval head.  No cumsum, no
+//     atomics, summation in sort order: bit-reproducible.
+//   kFused:  acc += depth_t[pixel, d] * feat_t[pixel, :]   (K4: the frustum tensor
+//            of src/modules.py:84 is never formed)
+//   !kFused: acc += x[point, :]                             (K4a)
 // --------------------------------------------------------------------------
 struct PoolFwdArgs {
-  const float* depth_t;           // (BN*HW, D)        fused
-  const float4* feat_t;           // (BN*HW, G)        fused
-  const float4* x;                // (P, G)            dense
-  const int32_t* sorted_points;   // (P) first K valid
-  const int32_t* sorted_cells;    // (P) output cell of each sorted point, first K valid
-  const int32_t* counts;          // {K, V}
-  const int2* cell_range;         // (n_cells) start >= end: empty
-  float4* bev;
-  uint32_t n_cells;
-  int G, D, HW;
-  int fill_warps;                 // warps per CTA that zero-fill (the rest reduce)
-  FastDiv div_g, div_dhw, div_hw;
+  const float* depth_t;           // (BN*HW, D)   fused
+  const float* feat_t;            // (BN*HW, C)   fused
+  const float* x;                 // (P, C)       dense
+  const int32_t* sorted_points;   // (P) sorted by output cell, ascending point id inside a cell
+  const int32_t* sorted_cells;    // (P) output cell of each sorted point, -1 beyond the K kept points
+  const int32_t* cell_start;      // (n_cells + 1)
+  float* bev;                     // (n_cells, C)
+  long long P;
+  int n_cells;
+  int fill_ctas;                  // CTAs [0, fill_ctas) zero-fill, the rest reduce
+  int C, D, HW;
+  FastDiv div_dhw, div_hw, div_g4;
 };
 
 constexpr int kPoolThreads = 256;
 constexpr int kPoolWarps = kPoolThreads / 32;
+constexpr int kPoolChunk = 32;    // sorted points per reduce warp
+constexpr int kPoolRec = 64;      // staged records per warp: the chunk + the tail of its last interval
 
-template <bool kFused, int kLanes>
+template <int kVec> struct VecOf;
+template <> struct VecOf<1> { using type = float; };
+template <> struct VecOf<2> { using type = float2; };
+template <> struct VecOf<4> { using type = float4; };
+
+template <int kVec> __device__ __forceinline__ void vec_zero(typename VecOf<kVec>::type& v);
+template <> __device__ __forceinline__ void vec_zero<1>(float& v) { v = 0.f; }
+template <> __device__ __forceinline__ void vec_zero<2>(float2& v) { v = make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ void vec_zero<4>(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ void vec_fma(float d, const float& f, float& a) { a = fmaf(d, f, a); }
+__device__ __forceinline__ void vec_fma(float d, const float2& f, float2& a) {
+  a.x = fmaf(d, f.x, a.x); a.y = fmaf(d, f.y, a.y);
+}
+__device__ __forceinline__ void vec_fma(float d, const float4& f, float4& a) {
+  a.x = fmaf(d, f.x, a.x); a.y = fmaf(d, f.y, a.y); a.z = fmaf(d, f.z, a.z); a.w = fmaf(d, f.w, a.w);
+}
+
+template <bool kFused, int kVec>
 __global__ void __launch_bounds__(kPoolThreads)
 pool_fwd_nhwc_kernel(PoolFwdArgs a) {
-  constexpr int kGroups = 32 / kLanes;
-  constexpr uint32_t kLaneBits = (kLanes == 32) ? 0xffffffffu : ((1u << kLanes) - 1u);
+  using V = typename VecOf<kVec>::type;
+  constexpr int kU = 4;                                      // gathers per pipeline stage
+  constexpr int kS = kVec == 4 ? 2 : 4;                      // stages: (kS - 1) * kU gathers in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane == 0) phase_stamp_any(2, warp * 2);
 
-  // ---- FILL: zeros into empty voxels (dedicated warps; pure stores that overlap the gathers) ----
-  // One coalesced load fetches the intervals of 32 consecutive cells (the next block of 32 is
-  // prefetched before the stores go out); the emptiness bits are shared with a ballot and the
-  // cells' 32*G float4 are covered by G full-warp stores.
-  if (warp < a.fill_warps) {
-    if (warp == 0 && lane == 0) phase_stamp_any(2, 0);
-    const uint32_t n_fill = gridDim.x * static_cast<uint32_t>(a.fill_warps);
-    uint32_t c0 = (blockIdx.x * a.fill_warps + warp) * 32u;
-    int2 r = (c0 + lane < a.n_cells) ? __ldg(a.cell_range + c0 + lane) : make_int2(0, 1);
-    while (c0 < a.n_cells) {
-      const uint32_t c1 = c0 + n_fill * 32u;
-      const int2 rn = (c1 + lane < a.n_cells) ? __ldg(a.cell_range + c1 + lane) : make_int2(0, 1);
-      const uint32_t empty = __ballot_sync(0xffffffffu, r.x >= r.y);
+  // ======================= FILL: zeros into the empty voxels ==========================
+  if (static_cast<int>(blockIdx.x) < a.fill_ctas) {
+    const int n_blocks = (a.n_cells + 31) >> 5;
+    const int stride = a.fill_ctas * kPoolWarps;
+    const int G4 = a.C >> 2;                                 // float4 per line
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int blk = blockIdx.x * kPoolWarps + warp;
+    if (blk >= n_blocks) return;
+    auto bounds = [&](int bk, int& lo, int& hi) {
+      const int c = (bk << 5) + lane;
+      lo = 0; hi = 1;                                        // beyond the map: not ours to write
+      if (c < a.n_cells) { lo = __ldg(a.cell_start + c); hi = __ldg(a.cell_start + c + 1); }
+    };
+    int lo, hi;
+    bounds(blk, lo, hi);
+    while (true) {
+      const int nxt = blk + stride;
+      int nlo = 0, nhi = 1;
+      if (nxt < n_blocks) bounds(nxt, nlo, nhi);             // prefetch before the stores go out
+      const uint32_t empty = __ballot_sync(0xffffffffu, hi == lo);
       if (empty) {
-        float4* dst = a.bev + (size_t)c0 * a.G;
-        for (int k = 0; k < a.G; ++k) {
-          const uint32_t e = k * 32u + lane;
-          const uint32_t cl = a.div_g.div(e);
-          if ((empty >> cl) & 1u) st_stream_f4(dst + e, zero4);
+        float4* dst = reinterpret_cast<float4*>(a.bev + (size_t)(blk << 5) * a.C);
+        const int n4 = 32 * G4;
+        if (empty == 0xffffffffu) {
+          for (int e = lane; e < n4; e += 32) dst[e] = z4;
+        } else {
+          for (int e = lane; e < n4; e += 32) {
+            const uint32_t line = a.div_g4.div(static_cast<uint32_t>(e));
+            if ((empty >> line) & 1u) dst[e] = z4;
+          }
         }
       }
-      r = rn;
-      c0 = c1;
+      if (nxt >= n_blocks) break;
+      blk = nxt; lo = nlo; hi = nhi;
     }
-    if (warp == 0 && lane == 0) phase_stamp_any(2, 1);
+    if (lane == 0) phase_stamp_any(2, warp * 2 + 1);
     return;
   }
 
-  // ---- REDUCE: segmented sums over the sorted points --------------------------
-  // A group of kLanes lanes owns the intervals that START inside its chunk of kLanes sorted
-  // points.  Per pass: one cooperative load (point id, output cell, depth); the decoded records
-  // {cell, feature-row offset, depth} go to shared memory and two group ballots (valid points,
-  // interval heads) drive the walk, which reads one broadcast LDS.128 per point and has no
-  // per-point bounds logic.  The tail of the last interval is followed into the next chunk in
-  // steps of 4 points, where it only accumulates up to the first foreign head.  The kernel is
-  // latency-bound (dependent gathers), so it is kept lean in registers: 8 CTAs stay resident
-  // per SM and supply the parallelism.
-  __shared__ int4 s_rec[kPoolWarps][32];
-  const int rw = warp - a.fill_warps, n_rw = kPoolWarps - a.fill_warps;
-  const int grp = lane / kLanes, sub = lane % kLanes;
-  const uint32_t gmask = kLaneBits << (grp * kLanes);
-  const int K = __ldg(a.counts);
-  const int n_chunks = (K + kLanes - 1) / kLanes;
-  const int slot = (blockIdx.x * n_rw + rw) * kGroups + grp;
-  const int n_slots = gridDim.x * n_rw * kGroups;
-  const bool lane_active = sub < a.G;  // kLanes may exceed G (e.g. C = 80: 20 of 32 lanes)
-  int4* rec = &s_rec[warp][grp * kLanes];
-  const float4* src_lane = (kFused ? a.feat_t : a.x) + sub;   // this lane's float4 column of a row
-  float4* bev_lane = a.bev + sub;
-  const uint32_t G = static_cast<uint32_t>(a.G);
-
-  for (int chunk = slot; chunk < n_chunks; chunk += n_slots) {
-    int base = chunk * kLanes;
-    int width = kLanes;      // points loaded per pass: a full chunk first, then 4 at a time
-    int cur_cell = -1;
-    float4 acc = zero4;
-    bool first = true;
-    while (true) {
-      // cooperative load of `width` consecutive sorted points
-      const int i = base + sub;
-      const bool valid = (sub < width) && (i < K);
-      const int32_t pt = valid ? __ldg(a.sorted_points + i) : 0;
-      const int32_t cell = valid ? __ldg(a.sorted_cells + i) : -1;
-      int32_t prev = __shfl_up_sync(gmask, cell, 1, kLanes);
-      if (sub == 0) prev = (valid && i > 0) ? __ldg(a.sorted_cells + i - 1) : -1;
-      const bool head = valid && (cell != prev);
-      uint32_t row;   // feature row (pixel, or point for the dense variant)
-      float dv = 0.f;
-      if (kFused) {
-        uint32_t bn, rem, d, hw;
-        a.div_dhw.divmod(static_cast<uint32_t>(pt), bn, rem);
-        a.div_hw.divmod(rem, d, hw);
-        row = bn * a.HW + hw;
-        if (valid) dv = __ldg(a.depth_t + (size_t)row * a.D + d);
-      } else {
-        row = static_cast<uint32_t>(pt);
-        dv = 1.f;
-      }
-      __syncwarp(gmask);   // the previous pass is done reading the records
-      rec[sub] = make_int4(cell, static_cast<int>(row * G), __float_as_int(dv), 0);
-      const uint32_t vbits = (__ballot_sync(gmask, valid) >> (grp * kLanes)) & kLaneBits;
-      const uint32_t hbits = (__ballot_sync(gmask, head) >> (grp * kLanes)) & kLaneBits;
-      __syncwarp(gmask);
-      const int n_valid = __popc(vbits);   // valid points are a prefix of the pass
-      int j_begin, j_end;
-      if (first) {        // own chunk: start at the first head, run to the end of the data in it
-        j_begin = hbits ? (__ffs(hbits) - 1) : n_valid;
-        j_end = n_valid;
-      } else {            // continuation: only the points before the first foreign head
-        j_begin = 0;
-        j_end = hbits ? (__ffs(hbits) - 1) : n_valid;
-      }
-#pragma unroll 4
-      for (int j = j_begin; j < j_end; ++j) {
-        const int4 r = rec[j];
-        const float4 f = lane_active ? ldg_f4(src_lane + static_cast<uint32_t>(r.y)) : zero4;
-        if (first && ((hbits >> j) & 1u)) {      // a new interval starts: close the running one
-          if (cur_cell >= 0 && lane_active) st_stream_f4(bev_lane + static_cast<uint32_t>(cur_cell) * G, acc);
-          acc = zero4;
-          cur_cell = r.x;
-        }
-        const float d = __int_as_float(r.z);
-        acc.x = fmaf(d, f.x, acc.x);
-        acc.y = fmaf(d, f.y, acc.y);
-        acc.z = fmaf(d, f.z, acc.z);
-        acc.w = fmaf(d, f.w, acc.w);
-      }
-      // the open interval continues iff this pass was full and ended without meeting its end
-      if (cur_cell < 0 || j_end < width) break;
-      first = false;
-      base += width;
-      width = 4;
-    }
-    if (cur_cell >= 0 && lane_active) st_stream_f4(bev_lane + static_cast<uint32_t>(cur_cell) * G, acc);
+  // ======================= REDUCE: segmented sums over the sorted points ==============
+  __shared__ uint4 s_off[kPoolWarps][kPoolRec / 4];          // feature-row offset (16-byte units)
+  __shared__ float4 s_dep[kPoolWarps][kPoolRec / 4];         // depth probability
+  __shared__ int s_cell[kPoolWarps][kPoolChunk];             // output cell (heads only lie in the chunk)
+  const long long i0 = ((long long)(blockIdx.x - a.fill_ctas) * kPoolWarps + warp) * kPoolChunk;
+  if (i0 >= a.P) return;
+  const long long i = i0 + lane;
+  // one round of loads: this chunk's and the next chunk's ids and cells, and the cell before the chunk
+  int cell = -1, ncell = -1, pt = 0, npt = 0;
+  if (i < a.P) cell = __ldg(a.sorted_cells + i);
+  if (i + kPoolChunk < a.P) ncell = __ldg(a.sorted_cells + i + kPoolChunk);
+  int prev = (lane == 0 && i0 > 0) ? __ldg(a.sorted_cells + i0 - 1) : -1;
+  if (i < a.P) pt = __ldg(a.sorted_points + i);
+  if (i + kPoolChunk < a.P) npt = __ldg(a.sorted_points + i + kPoolChunk);
+  {
+    const int up = __shfl_up_sync(0xffffffffu, cell, 1);
+    if (lane > 0) prev = up;
   }
+  const uint32_t hb = __ballot_sync(0xffffffffu, cell >= 0 && cell != prev);   // interval heads
+  if (hb == 0u) { if (lane == 0) phase_stamp_any(2, warp * 2 + 1); return; }   // an earlier warp owns all of it
+  const uint32_t vb = __ballot_sync(0xffffffffu, cell >= 0);  // kept points are a prefix of the chunk
+  const int nv = __popc(vb);
+  const int h0 = __ffs(hb) - 1;                              // first owned point
+  const int last_cell = __shfl_sync(0xffffffffu, cell, nv - 1);
+  // tail of the last interval inside the next chunk (a prefix of it)
+  const uint32_t cont = __ballot_sync(0xffffffffu, nv == kPoolChunk && ncell == last_cell);
+  const int tail = (cont == 0xffffffffu) ? 32 : __ffs(~cont) - 1;
+  const int n_rec = nv - h0 + tail;                          // records to walk: [h0, nv) + tail
+
+  const uint32_t nact = static_cast<uint32_t>(a.C / kVec);   // lanes that own channels
+  const bool active = lane < nact;                           // idle lanes (C < 32 * kVec) shadow lane 0:
+  const uint32_t vlane = active ? lane : 0u;                 // they gather valid data and never store
+  const char* src = reinterpret_cast<const char*>(reinterpret_cast<const V*>(kFused ? a.feat_t : a.x) + vlane);
+  const uint32_t row16 = static_cast<uint32_t>(a.C) >> 2;    // 16-byte units per feature row
+  auto gather = [&](uint32_t off16) { return __ldg(reinterpret_cast<const V*>(src + ((size_t)off16 << 4))); };
+  V* out = reinterpret_cast<V*>(a.bev) + vlane;
+  uint32_t* offs = reinterpret_cast<uint32_t*>(s_off[warp]);
+  float* deps = reinterpret_cast<float*>(s_dep[warp]);
+
+  // ---- stage the records, shifted so that the first owned point is record 0 ----
+  auto record = [&](int p, uint32_t& off16, float& dv) {
+    if (kFused) {
+      uint32_t bn, rem, d, hw;
+      a.div_dhw.divmod(static_cast<uint32_t>(p), bn, rem);
+      a.div_hw.divmod(rem, d, hw);
+      const uint32_t row = bn * a.HW + hw;
+      off16 = row * row16;
+      dv = __ldg(a.depth_t + (size_t)row * a.D + d);
+    } else {
+      off16 = static_cast<uint32_t>(p) * row16;
+      dv = 1.0f;
+    }
+  };
+  {
+    uint32_t o0 = 0, o1 = 0;
+    float d0 = 0.f, d1 = 0.f;
+    const bool own0 = lane >= h0 && lane < nv, own1 = lane < tail;
+    if (own0) record(pt, o0, d0);
+    if (own1) record(npt, o1, d1);
+    if (own0) { offs[lane - h0] = o0; deps[lane - h0] = d0; }
+    if (own1) { offs[nv - h0 + lane] = o1; deps[nv - h0 + lane] = d1; }
+    s_cell[warp][lane] = cell;
+  }
+  __syncwarp();
+
+  // ---- walk: software pipeline over groups of kU records ----
+  const uint32_t heads = hb >> h0;                           // bit r: record r starts an interval (bit 0 set)
+  int cur = s_cell[warp][h0];
+  V acc;
+  vec_zero<kVec>(acc);
+  auto issue = [&](int r, V (&f)[kU]) {
+    const uint4 o4 = s_off[warp][r >> 2];
+    f[0] = gather(o4.x);
+    f[1] = gather(o4.y);
+    f[2] = gather(o4.z);
+    f[3] = gather(o4.w);
+  };
+  auto consume = [&](int r, const V (&f)[kU]) {
+    const float4 d4 = s_dep[warp][r >> 2];
+    const float d[kU] = {d4.x, d4.y, d4.z, d4.w};
+    const uint32_t hm = (r < 32) ? ((heads >> r) & 0xfu) : 0u;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (((hm >> u) & 1u) && (r + u) > 0) {                 // warp-uniform: a new interval starts
+        if (active) out[(size_t)cur * nact] = acc;
+        vec_zero<kVec>(acc);
+        cur = s_cell[warp][h0 + r + u];
+      }
+      vec_fma(d[u], f[u], acc);
+    }
+  };
+  const int n_full = n_rec & ~(kU - 1);
+  if (n_full > 0) {
+    V f[kS][kU];
+#pragma unroll
+    for (int st = 0; st < kS - 1; ++st)
+      if (st * kU < n_full) issue(st * kU, f[st]);
+    for (int r0 = 0; r0 < n_full; r0 += kS * kU) {
+#pragma unroll
+      for (int st = 0; st < kS; ++st) {
+        const int r = r0 + st * kU;
+        if (r < n_full) {
+          if (r + (kS - 1) * kU < n_full) issue(r + (kS - 1) * kU, f[(st + kS - 1) % kS]);
+          consume(r, f[st]);
+        }
+      }
+    }
+  }
+  for (int r = n_full; r < n_rec; ++r) {                     // at most kU - 1 records
+    const V f = gather(offs[r]);
+    if (r < 32 && ((heads >> r) & 1u) && r > 0) {
+      if (active) out[(size_t)cur * nact] = acc;
+      vec_zero<kVec>(acc);
+      cur = s_cell[warp][h0 + r];
+    }
+    vec_fma(deps[r], f, acc);
+  }
+  // ---- an interval longer than the look-ahead (adversarial inputs): follow it to its end ----
+  if (tail == 32) {
+    for (long long j = i0 + 2 * kPoolChunk; j < a.P; ++j) {
+      if (__ldg(a.sorted_cells + j) != last_cell) break;
+      uint32_t o;
+      float dv;
+      record(__ldg(a.sorted_points + j), o, dv);
+      vec_fma(dv, gather(o), acc);
+    }
+  }
+  if (active) out[(size_t)cur * nact] = acc;
+  if (lane == 0) phase_stamp_any(2, warp * 2 + 1);
 }
 
 // --------------------------------------------------------------------------
@@ -291,20 +370,21 @@ pool_dense_bwd_nhwc_kernel(const float4* __restrict__ dbev, const int32_t* __res
 // --------------------------------------------------------------------------
 // K5 fused backward, channels-innermost dBEV.
 //
-// One CTA per feature-map row (bn, h): its fW pixels x D depth bins.  A warp
-// owns one pixel at a time and keeps that pixel's context vector in registers;
-// kLanes lanes (a power of two >= C/4) cooperate on one point, 32/kLanes points
-// sit side by side in the warp and kUnroll such steps are issued back to back,
-// so up to kUnroll*32/kLanes voxel-gradient lines are in flight per warp.
-// For every kept point the voxel gradient g (C floats, one contiguous line of
-// the channels-innermost dBEV) is gathered once and used twice:
+// A warp owns one pixel (bn, h, w): its context vector stays in registers while
+// the warp walks the pixel's D depth bins.  kLanes lanes (a power of two >= C/4)
+// cooperate on one point, 32/kLanes points sit side by side in the warp and
+// kUnroll such steps are issued back to back, so kUnroll*32/kLanes voxel-gradient
+// lines are in flight per warp.  For every kept point the voxel gradient g (one
+// contiguous line of the channels-innermost dBEV) is gathered once and used twice:
 //     d_depth[d] = <g, feat>      d_feat += depth[d] * g
-// Only OCCUPIED voxels of dBEV are ever read.  <g, feat> has C terms of order
-// one that cancel, so it is accumulated in float64 (B200 has the FP64 pipe) and
-// the kUnroll partial dots of a lane are reduced together with a transposed
-// butterfly (2*kUnroll shuffles instead of kUnroll*log2(kLanes)).  Results are
-// staged in shared memory and written as whole (d, :) / (c, :) rows.  No
-// atomics anywhere: bit-reproducible.
+// Only OCCUPIED voxels of dBEV are ever read.  <g, feat> has C terms of order one
+// that cancel, so it is accumulated in float64 and the kUnroll partial dots of a
+// lane are reduced together with a transposed butterfly (2*kUnroll shuffles
+// instead of kUnroll*log2(kLanes)).  The warps of a CTA are the fH pixels of one
+// image column (bn, w): along a camera ray they fall into the same BEV cells
+// (Z is collapsed), so the column's voxel lines are fetched from L2 once and
+// re-used out of L1.  There is no CTA-wide phase and no atomics: warps run
+// independently and results are bit-reproducible.
 // --------------------------------------------------------------------------
 struct PoolBwdArgs {
   const float4* dbev;       // (n_cells, G)
@@ -314,37 +394,34 @@ struct PoolBwdArgs {
   float* ddepth;            // (BN, D, fH, fW)
   float* dfeat;             // (BN, C, fH, fW)
   int D, fH, fW, C, G;
+  int n_pix;                // BN * fH * fW
+  FastDiv div_fh, div_fw;
 };
 
+constexpr int kBwdThreads = 256;
+constexpr int kBwdWarps = kBwdThreads / 32;
+constexpr int kBwdChunk = 128;   // depth bins staged per warp at a time
+
 template <int kLanes>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(kBwdThreads, 3)
 liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
   constexpr int kPts = 32 / kLanes;                 // points per warp step
   constexpr int kUnroll = kLanes >= 8 ? 8 : kLanes; // steps in flight
   constexpr int kRound = kPts * kUnroll;            // depth bins per round
   constexpr int kLog = kLanes == 32 ? 5 : kLanes == 16 ? 4 : kLanes == 8 ? 3 : 2;
   constexpr int kLogU = kUnroll == 8 ? 3 : 2;
-  const int bn = blockIdx.x / a.fH, h = blockIdx.x % a.fH;
+  static_assert(kBwdChunk % kRound == 0, "chunk must hold whole rounds");
+  __shared__ int2 s_cd[kBwdWarps][kBwdChunk];       // {output cell, depth bits} of the staged bins
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // pixel of this warp: h fastest, so a CTA is one image column (bn, w) when fH == 8
+  const uint32_t q = blockIdx.x * kBwdWarps + warp;
+  if (q >= static_cast<uint32_t>(a.n_pix)) return;
+  uint32_t t, h, bn, w;
+  a.div_fh.divmod(q, t, h);
+  a.div_fw.divmod(t, bn, w);
   const int HW = a.fH * a.fW;
-  // depth bins are padded to a whole number of rounds ({-1, 0} = dropped point), so the
-  // main loop needs no bounds checks at all
-  const int Dpad = (a.D + kRound - 1) / kRound * kRound;
-  int2* s_cd = reinterpret_cast<int2*>(s_raw);            // [Dpad][fW] {output cell, depth bits}
-  float* s_dd = reinterpret_cast<float*>(s_cd + Dpad * a.fW);  // [Dpad][fW]
-  float* s_df = s_dd + Dpad * a.fW;                       // [C][fW+1]
-  const int dfs = a.fW + 1;
-  for (int i = threadIdx.x; i < Dpad * a.fW; i += blockDim.x) {
-    const int d = i / a.fW, w = i - d * a.fW;
-    int2 v = make_int2(-1, 0);
-    if (d < a.D) {
-      v.x = __ldg(a.cells + ((size_t)(bn * a.D + d) * a.fH + h) * a.fW + w);
-      v.y = __float_as_int(__ldg(a.depth_t + ((size_t)bn * HW + h * a.fW + w) * a.D + d));
-    }
-    s_cd[i] = v;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const uint32_t pix = bn * HW + h * a.fW + w;
   const int grp = lane / kLanes, sub = lane % kLanes;
   const bool lane_active = sub < a.G;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -354,23 +431,34 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
   for (int k = 0; k < kLogU; ++k)
     if (sub & (kLanes >> (k + 1))) my_u += kUnroll >> (k + 1);
   const bool writer = (sub & ((kLanes >> kLogU) - 1)) == 0;
-  const float4* gbase = a.dbev + sub;                 // this lane's float4 column of every voxel line
   const uint32_t G = static_cast<uint32_t>(a.G);
-  const int step = kPts * a.fW;                       // shared-memory stride between unrolled steps
+  const float4* gbase = a.dbev + sub;                 // this lane's float4 column of every voxel line
+  const float4 f = lane_active ? ldg_f4(a.feat_t + pix * G + sub) : zero4;
+  const double fx = f.x, fy = f.y, fz = f.z, fw = f.w;
+  float4 acc = zero4;
+  int2* cd = s_cd[warp];
+  const size_t col = (size_t)h * a.fW + w;            // offset of the pixel inside a (fH, fW) slice
 
-  for (int w = warp; w < a.fW; w += nwarps) {
-    const uint32_t pix = static_cast<uint32_t>(bn * HW + h * a.fW + w);
-    const float4 f = lane_active ? ldg_f4(a.feat_t + pix * G + sub) : zero4;
-    const double fx = f.x, fy = f.y, fz = f.z, fw = f.w;
-    float4 acc = zero4;
-    const int2* cd = s_cd + grp * a.fW + w;
-    float* dd = s_dd + (my_u * kPts + grp) * a.fW + w;
-    for (int d0 = 0; d0 < Dpad; d0 += kRound, cd += kRound * a.fW, dd += kRound * a.fW) {
+  for (int dc = 0; dc < a.D; dc += kBwdChunk) {
+    const int nd = min(kBwdChunk, a.D - dc);
+    const int nd_pad = (nd + kRound - 1) / kRound * kRound;
+    __syncwarp();
+    for (int l = lane; l < nd_pad; l += 32) {
+      int2 v = make_int2(-1, 0);                      // padding = dropped point
+      if (l < nd) {
+        const int d = dc + l;
+        v.x = __ldg(a.cells + ((size_t)bn * a.D + d) * HW + col);
+        v.y = __float_as_int(__ldg(a.depth_t + (size_t)pix * a.D + d));
+      }
+      cd[l] = v;
+    }
+    __syncwarp();
+    for (int d0 = 0; d0 < nd_pad; d0 += kRound) {
       float4 g[kUnroll];
       float dv[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const int2 v = cd[u * step];
+        const int2 v = cd[d0 + u * kPts + grp];
         dv[u] = __int_as_float(v.y);
         const uint32_t off = static_cast<uint32_t>(v.x) * G;   // n_cells * G < 2^31 (checked by the host)
         g[u] = (v.x >= 0 && lane_active) ? ldg_f4(gbase + off) : zero4;
@@ -378,11 +466,11 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
       double dot[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        double t = static_cast<double>(g[u].x) * fx;
-        t = fma(static_cast<double>(g[u].y), fy, t);
-        t = fma(static_cast<double>(g[u].z), fz, t);
-        t = fma(static_cast<double>(g[u].w), fw, t);
-        dot[u] = t;
+        double s = static_cast<double>(g[u].x) * fx;
+        s = fma(static_cast<double>(g[u].y), fy, s);
+        s = fma(static_cast<double>(g[u].z), fz, s);
+        s = fma(static_cast<double>(g[u].w), fw, s);
+        dot[u] = s;
         acc.x = fmaf(dv[u], g[u].x, acc.x);
         acc.y = fmaf(dv[u], g[u].y, acc.y);
         acc.z = fmaf(dv[u], g[u].z, acc.z);
@@ -405,29 +493,21 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
           dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
         }
       }
-      if (writer) *dd = static_cast<float>(dot[0]);   // rows beyond D are padding
+      const int d = dc + d0 + my_u * kPts + grp;
+      if (writer && d < a.D) a.ddepth[((size_t)bn * a.D + d) * HW + col] = static_cast<float>(dot[0]);
     }
-    // fold the kPts point-groups of the warp together
+  }
+  // fold the kPts point-groups of the warp together
 #pragma unroll
-    for (int o = kLanes; o < 32; o <<= 1) {
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if (grp == 0 && lane_active) {
-      float* df = s_df + (sub * 4) * dfs + w;
-      df[0] = acc.x; df[dfs] = acc.y; df[2 * dfs] = acc.z; df[3 * dfs] = acc.w;
-    }
+  for (int o = kLanes; o < 32; o <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < a.D * a.fW; i += blockDim.x) {
-    const int d = i / a.fW, w = i - d * a.fW;
-    a.ddepth[((size_t)(bn * a.D + d) * a.fH + h) * a.fW + w] = s_dd[i];
-  }
-  for (int i = threadIdx.x; i < a.C * a.fW; i += blockDim.x) {
-    const int c = i / a.fW, w = i - c * a.fW;
-    a.dfeat[((size_t)(bn * a.C + c) * a.fH + h) * a.fW + w] = s_df[c * dfs + w];
+  if (grp == 0 && lane_active) {
+    float* df = a.dfeat + ((size_t)bn * a.C + sub * 4) * HW + col;
+    df[0] = acc.x; df[HW] = acc.y; df[2 * (size_t)HW] = acc.z; df[3 * (size_t)HW] = acc.w;
   }
 }
 

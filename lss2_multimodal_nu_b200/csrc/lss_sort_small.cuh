@@ -310,284 +310,4 @@ inline int run_sort_passes_small(const SortPlan& s, const int32_t* keys, int32_t
   return LSS_OK;
 }
 
-// ===========================================================================
-// Plan path, single wave:  P1 = one stable MSD partition on the high `hi_bits`
-// of the rank (radix_pass_small_kernel, geometry fused, dropped points filtered
-// out), P2 = local_sort_intervals_kernel below: one CTA per bucket finishes the
-// sort on the low `lo_bits` entirely in shared memory (no cross-CTA traffic) and,
-// because a bucket's low-digit histogram IS the per-cell point count, writes the
-// [start, end) interval of every cell of the bucket (K3) as a by-product.
-// Final order == the LSD order: rank ascending, ties in ascending point index.
-// ===========================================================================
-constexpr int kLocalThreads = 256;
-constexpr int kLocalWarps = kLocalThreads / 32;
-constexpr int kLocalItems = 8;
-constexpr int kLocalChunk = kLocalThreads * kLocalItems;  // 2048 keys
-constexpr int kLocalMaxBits = 11;
-constexpr int kLocalMaxBins = 1 << kLocalMaxBits;
-constexpr int kLocalBinsPerThread = kLocalMaxBins / kLocalThreads;  // 8
-
-struct LocalArgs {
-  const int32_t* keys;          // partitioned ranks (P1 output)
-  const int32_t* vals;          // partitioned point indices
-  const uint32_t* bucket_start; // [n_buckets + 1]
-  int32_t* sorted_points;       // final order (first K entries)
-  int32_t* sorted_ranks;        // or null
-  int32_t* sorted_cells;        // output cell of each sorted point
-  int2* cell_range;             // every cell of the grid is written (empty: 0,0)
-  int32_t* counts;              // {K, V}, zero on entry
-  GridDev g;
-  FastDiv div_b, div_z, div_y;
-  int lo_bits;
-};
-
-__global__ void __launch_bounds__(kLocalThreads)
-local_sort_intervals_kernel(LocalArgs a) {
-  __shared__ uint16_t s_wh[kLocalWarps][kLocalMaxBins + 2];
-  __shared__ uint32_t s_start[kLocalMaxBins];  // counts, then running start per bin
-  __shared__ uint32_t s_warp_tot[kLocalWarps];
-  __shared__ int s_kv[2];
-  extern __shared__ int32_t s_cell[];  // [nbins] output cell of each bin's rank (dynamic)
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nbins = 1 << a.lo_bits;
-  const uint32_t mask = static_cast<uint32_t>(nbins - 1);
-  const int bucket = blockIdx.x;
-  const uint32_t begin = a.bucket_start[bucket], end = a.bucket_start[bucket + 1];
-  const uint32_t n = end - begin;
-  phase_stamp(1, 0);
-
-  for (int i = tid; i < nbins; i += kLocalThreads) s_start[i] = 0;
-  {
-    uint32_t* z = reinterpret_cast<uint32_t*>(&s_wh[0][0]);
-    constexpr int kWords = kLocalWarps * (kLocalMaxBins + 2) / 2;
-    for (int i = tid; i < kWords; i += kLocalThreads) z[i] = 0;
-  }
-  if (tid < 2) s_kv[tid] = 0;
-  __syncthreads();
-
-  phase_stamp(1, 1);
-  // ---- sweep 1: low-digit histogram of the bucket (keys of the first chunk stay in registers)
-  int32_t key[kLocalItems], val[kLocalItems];
-#pragma unroll
-  for (int j = 0; j < kLocalItems; ++j) {
-    const uint32_t i = warp * (32 * kLocalItems) + j * 32 + lane;
-    key[j] = (i < n) ? a.keys[begin + i] : 0;
-    val[j] = (i < n) ? a.vals[begin + i] : 0;
-  }
-#pragma unroll
-  for (int j = 0; j < kLocalItems; ++j) {
-    const uint32_t i = warp * (32 * kLocalItems) + j * 32 + lane;
-    if (i < n) atomicAdd(&s_start[static_cast<uint32_t>(key[j]) & mask], 1u);
-  }
-  for (uint32_t i = kLocalChunk + tid; i < n; i += kLocalThreads)
-    atomicAdd(&s_start[static_cast<uint32_t>(a.keys[begin + i]) & mask], 1u);
-  __syncthreads();
-
-  phase_stamp(1, 2);
-  // ---- exclusive scan over bins; every bin is one rank, i.e. one cell: write its interval
-  {
-    const int per = nbins >= kLocalThreads ? nbins / kLocalThreads : 1;
-    uint32_t local[kLocalBinsPerThread];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < kLocalBinsPerThread; ++k) {
-      const int bin = tid * per + k;
-      local[k] = (k < per && bin < nbins) ? s_start[bin] : 0u;
-      sum += local[k];
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < warp; ++w) woff += s_warp_tot[w];
-    uint32_t run = woff + incl - sum;
-    int kept = 0, occupied = 0;
-#pragma unroll
-    for (int k = 0; k < kLocalBinsPerThread; ++k) {
-      const int bin = tid * per + k;
-      if (k < per && bin < nbins) {
-        s_start[bin] = run;
-        const int32_t r = static_cast<int32_t>((static_cast<uint32_t>(bucket) << a.lo_bits) | static_cast<uint32_t>(bin));
-        s_cell[bin] = -1;
-        if (r < a.g.n_cells) {
-          // rank = ((x*Y + y)*Z + z)*B + b  ->  output cell ((b*X + x)*Y + y)*Z + z
-          uint32_t t0, b, t1, z, x, y;
-          a.div_b.divmod(static_cast<uint32_t>(r), t0, b);
-          a.div_z.divmod(t0, t1, z);
-          a.div_y.divmod(t1, x, y);
-          const int32_t cell = ((static_cast<int32_t>(b) * a.g.nx[0] + static_cast<int32_t>(x)) * a.g.nx[1] +
-                                static_cast<int32_t>(y)) * a.g.nx[2] + static_cast<int32_t>(z);
-          s_cell[bin] = cell;
-          const int s0 = static_cast<int>(begin + run);
-          a.cell_range[cell] = local[k] ? make_int2(s0, s0 + static_cast<int>(local[k])) : make_int2(0, 0);
-          kept += static_cast<int>(local[k]);
-          occupied += local[k] ? 1 : 0;
-        }
-        run += local[k];
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      kept += __shfl_xor_sync(0xffffffffu, kept, o);
-      occupied += __shfl_xor_sync(0xffffffffu, occupied, o);
-    }
-    if (lane == 0 && kept) { atomicAdd(&s_kv[0], kept); atomicAdd(&s_kv[1], occupied); }
-  }
-  __syncthreads();
-  if (tid < 2 && s_kv[tid]) atomicAdd(&a.counts[tid], s_kv[tid]);
-  phase_stamp(1, 3);
-  if (n == 0) return;
-
-  // ---- sweep 2: stable rank + scatter, chunk by chunk (ascending input order) ----
-  for (uint32_t c0 = 0; c0 < n; c0 += kLocalChunk) {
-    if (c0) {
-#pragma unroll
-      for (int j = 0; j < kLocalItems; ++j) {
-        const uint32_t i = c0 + warp * (32 * kLocalItems) + j * 32 + lane;
-        key[j] = (i < n) ? a.keys[begin + i] : 0;
-        val[j] = (i < n) ? a.vals[begin + i] : 0;
-      }
-    }
-    uint16_t offs[kLocalItems];
-#pragma unroll
-    for (int j = 0; j < kLocalItems; ++j) {
-      const uint32_t i = c0 + warp * (32 * kLocalItems) + j * 32 + lane;
-      const uint32_t digit = (i < n) ? (static_cast<uint32_t>(key[j]) & mask) : static_cast<uint32_t>(nbins);
-      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-      const int leader = __ffs(peers) - 1;
-      const uint32_t below = __popc(peers & ((1u << lane) - 1u));
-      uint32_t old = 0;
-      if (lane == leader) {
-        old = s_wh[warp][digit];
-        s_wh[warp][digit] = static_cast<uint16_t>(old + __popc(peers));
-      }
-      old = __shfl_sync(0xffffffffu, old, leader);
-      offs[j] = static_cast<uint16_t>(old + below);
-      __syncwarp();
-    }
-    __syncthreads();
-    // scan the per-warp counts of each bin over warps; remember the chunk total
-    uint32_t chunk_tot[kLocalBinsPerThread];
-#pragma unroll
-    for (int k = 0; k < kLocalBinsPerThread; ++k) {
-      const int bin = tid + k * kLocalThreads;
-      chunk_tot[k] = 0;
-      if (bin < nbins) {
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < kLocalWarps; ++w) {
-          const uint32_t c = s_wh[w][bin];
-          s_wh[w][bin] = static_cast<uint16_t>(run);
-          run += c;
-        }
-        chunk_tot[k] = run;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kLocalItems; ++j) {
-      const uint32_t i = c0 + warp * (32 * kLocalItems) + j * 32 + lane;
-      if (i < n) {
-        const uint32_t digit = static_cast<uint32_t>(key[j]) & mask;
-        const uint32_t dst = begin + s_start[digit] + s_wh[warp][digit] + offs[j];
-        a.sorted_points[dst] = val[j];
-        if (a.sorted_ranks) a.sorted_ranks[dst] = key[j];
-        a.sorted_cells[dst] = s_cell[digit];
-      }
-    }
-    phase_stamp(1, 4 + (c0 ? 1 : 0));
-    if (c0 + kLocalChunk < n) {  // more chunks: advance the bin starts, clear the warp counters
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < kLocalBinsPerThread; ++k) {
-        const int bin = tid + k * kLocalThreads;
-        if (bin < nbins) {
-          s_start[bin] += chunk_tot[k];
-#pragma unroll
-          for (int w = 0; w < kLocalWarps; ++w) s_wh[w][bin] = 0;
-        }
-      }
-      if (tid < kLocalWarps) s_wh[tid][nbins] = 0;
-      __syncthreads();
-    }
-  }
-}
-
-inline int launch_local_sort(const LocalArgs& l, int n_buckets, cudaStream_t st) {
-  const size_t dyn = (size_t)(1 << l.lo_bits) * sizeof(int32_t);
-  static bool attr_set = false;
-  if (!attr_set) {  // static (41 KB) + dynamic (<= 8 KB) may exceed the 48 KB default
-    LSS_CUDA_TRY(cudaFuncSetAttribute(local_sort_intervals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kLocalMaxBins * sizeof(int32_t))), "cudaFuncSetAttribute(local sort)");
-    attr_set = true;
-  }
-  local_sort_intervals_kernel<<<n_buckets, kLocalThreads, dyn, st>>>(l);
-  LSS_LAUNCH_CHECK("local_sort_intervals_kernel");
-  return LSS_OK;
-}
-
-struct MsdPlan {
-  bool ok;
-  int lo_bits, hi_bits;
-  int n_buckets;
-  size_t off_bucket_start;  // inside the sort workspace, after the single-wave control words
-  size_t total_bytes;
-};
-
-// MSD split of the key bits: the low <= 11 bits are finished locally, the rest (<= 10 bits)
-// is the global partition.  Applies when the sort is single-wave and key_bits <= 21.
-inline MsdPlan make_msd_plan(const SortPlan& s) {
-  MsdPlan m;
-  memset(&m, 0, sizeof(m));
-  m.lo_bits = s.key_bits > kLocalMaxBits ? kLocalMaxBits : (s.key_bits > 1 ? s.key_bits - 1 : 1);
-  m.hi_bits = s.key_bits - m.lo_bits;
-  if (m.hi_bits < 1) m.hi_bits = 1;
-  m.ok = s.small && m.hi_bits <= kSmallMaxBitsPlan;
-  m.n_buckets = 1 << m.hi_bits;
-  m.off_bucket_start = s.total_bytes;
-  m.total_bytes = s.total_bytes + align_up((size_t)(m.n_buckets + 1) * 4, 256);
-  return m;
-}
-
-// P1 + P2.  Outputs: cells (P), sorted_points (first K valid), cell_range (all cells), counts.
-inline int run_msd_plan(const SortPlan& s, const MsdPlan& m, const SmallGeom& sg, int32_t* sorted_points,
-                        int32_t* sorted_cells, int32_t* cell_range, int32_t* counts, long long P, void* ws,
-                        cudaStream_t st) {
-  char* c = static_cast<char*>(ws);
-  int32_t* part_keys = reinterpret_cast<int32_t*>(c + s.off_tmp_keys);
-  int32_t* part_vals = reinterpret_cast<int32_t*>(c + s.off_tmp_vals);
-  uint32_t* bucket_start = reinterpret_cast<uint32_t*>(c + m.off_bucket_start);
-  SmallPassArgs a;
-  memset(&a, 0, sizeof(a));
-  a.keys_out = part_keys; a.vals_out = part_vals;
-  a.P = P; a.shift = m.lo_bits; a.bits = m.hi_bits; a.tiles = (int)s.tiles;
-  a.rows = reinterpret_cast<uint16_t*>(c + s.off_control);
-  a.flags = reinterpret_cast<uint32_t*>(c + s.off_flags);
-  a.ctl = reinterpret_cast<uint32_t*>(c + s.off_ctl);
-  a.drop_from = sg.grid.n_cells;
-  a.bucket_start = bucket_start; a.counts = counts;
-  a.geom = sg.geom; a.grid = sg.grid; a.cells = sg.cells;
-  const int hw = sg.geom.fH * sg.geom.fW;
-  a.div_ppc = FastDiv((uint32_t)(sg.geom.D * hw));
-  a.div_hw = FastDiv((uint32_t)hw);
-  a.div_w = FastDiv((uint32_t)sg.geom.fW);
-  radix_pass_small_kernel<true><<<(unsigned)s.tiles, kSmallThreads, 0, st>>>(a);
-  LSS_LAUNCH_CHECK("radix_pass_small_kernel<geom>");
-  LocalArgs l;
-  memset(&l, 0, sizeof(l));
-  l.keys = part_keys; l.vals = part_vals; l.bucket_start = bucket_start;
-  l.sorted_points = sorted_points; l.sorted_ranks = nullptr; l.sorted_cells = sorted_cells;
-  l.cell_range = reinterpret_cast<int2*>(cell_range); l.counts = counts;
-  l.g = sg.grid;
-  l.div_b = FastDiv(sg.grid.B); l.div_z = FastDiv(sg.grid.nx[2]); l.div_y = FastDiv(sg.grid.nx[1]);
-  l.lo_bits = m.lo_bits;
-  return launch_local_sort(l, m.n_buckets, st);
-}
-
 }  // namespace lss

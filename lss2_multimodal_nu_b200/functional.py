@@ -12,7 +12,8 @@ Mapping to the reference (paths relative to the reference root):
   quantize_rank       quantise, kept mask, ranks    src/model_baseline.py:92-109
   sort_ranks          ranks.argsort()               src/model_baseline.py:110
   intervals           QuickCumsum boundary mask     src/tools.py:196-197
-  build_plan          geometry half of get_voxels   src/model_baseline.py:128-131
+  build_plan          geometry half of get_voxels   src/model_baseline.py:128-131, :110,
+                                                    src/tools.py:196-197
   lift_splat          lift + voxel_pooling fwd/bwd  src/modules.py:84,
                                                     src/model_baseline.py:84-126,
                                                     src/tools.py:192-218
@@ -199,7 +200,11 @@ def intervals(sorted_ranks: torch.Tensor, grid: GridSpec, B: int, want_last_mask
 # --------------------------------------------------------------------------
 @dataclass
 class Plan:
-    """Per-batch index tables: depends on calibration + grid only, never on features."""
+    """Per-batch index tables: depends on calibration + grid only, never on features.
+
+    The point list is sorted by OUTPUT CELL ((b*X + x)*Y + y)*Z + z -- the reference's rank
+    (src/model_baseline.py:106-109) with the batch digit moved to the front -- stably, so every
+    voxel's run holds the reference's points in the reference's order (see reference_order())."""
     grid: GridSpec
     B: int
     N: int
@@ -207,9 +212,9 @@ class Plan:
     fH: int
     fW: int
     cells: torch.Tensor          # (P) int32 output cell of each point, -1 if dropped
-    sorted_points: torch.Tensor  # (P) int32 point index in rank order (first K entries valid)
-    sorted_cells: torch.Tensor   # (P) int32 output cell of each sorted point (first K valid)
-    cell_range: torch.Tensor     # (n_cells, 2) int32 [start, end) into sorted_points
+    cell_start: torch.Tensor     # (n_cells + 1) int32: cell c owns sorted_points[cell_start[c]:cell_start[c+1]]
+    sorted_points: torch.Tensor  # (P) int32 point ids ordered by (cell, point id); first K entries valid
+    sorted_cells: torch.Tensor   # (P) int32 output cell of each sorted point, -1 beyond the K kept points
     counts: torch.Tensor         # (2) int32 {K, V}
 
     @property
@@ -219,15 +224,27 @@ class Plan:
     def shape(self, C: int) -> _abi.LssShape:
         return _abi.make_shape(self.B, self.N, self.D, self.fH, self.fW, C)
 
+    def reference_order(self) -> torch.Tensor:
+        """The kept points in the order of the reference's ``ranks.argsort()``
+        (src/model_baseline.py:110): the plan's order with the batch digit moved back to the
+        least-significant place, via lss_sort_ranks (K2) on the reference's ranks."""
+        K = int(self.counts[0])
+        X, Y, Z = self.grid.nx
+        c = self.cells.long()
+        b, rest = c // (X * Y * Z), c % (X * Y * Z)
+        n_cells = self.grid.n_cells(self.B)
+        ranks = torch.where(c >= 0, rest * self.B + b, torch.full_like(c, n_cells)).int()
+        _, sp = sort_ranks(ranks.contiguous(), n_cells)
+        return sp[:K]
+
 
 _WORKSPACES: Dict[Tuple, torch.Tensor] = {}
 
 
-def _plan_workspace(dev, stream: int, shape: _abi.LssShape, g: _abi.LssGrid) -> torch.Tensor:
-    """Zero-initialised scratch, reused per (device, stream, problem size)."""
-    nbytes = _abi.load().lss_plan_workspace_bytes(shape, g)
+def _workspace(dev, stream: int, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch, reused per (device, stream, size)."""
     if nbytes == 0:
-        raise RuntimeError("lss_plan_workspace_bytes rejected the shape/grid")
+        raise RuntimeError("the plan workspace query rejected the shape/grid")
     key = (dev.index, stream, nbytes)
     ws = _WORKSPACES.get(key)
     if ws is None:
@@ -236,8 +253,16 @@ def _plan_workspace(dev, stream: int, shape: _abi.LssShape, g: _abi.LssGrid) -> 
     return ws
 
 
+def _plan_outputs(P: int, n_cells: int, dev):
+    return (torch.empty(P, dtype=torch.int32, device=dev),
+            torch.empty(n_cells + 1, dtype=torch.int32, device=dev),
+            torch.empty(P, dtype=torch.int32, device=dev),
+            torch.empty(P, dtype=torch.int32, device=dev),
+            torch.empty(2, dtype=torch.int32, device=dev))
+
+
 def build_plan(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: GridSpec) -> Plan:
-    """K0 -> K1' -> K2 -> K3 in one C call (lss_build_plan)."""
+    """K0 -> K1' -> counting sort -> intervals in one C call (lss_build_plan)."""
     dev = _need_cuda(us, vs, ds, rots, trans, intrins, post_rots, post_trans)
     B, N = trans.shape[0], trans.shape[1]
     D, fH, fW = ds.numel(), vs.numel(), us.numel()
@@ -245,32 +270,38 @@ def build_plan(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: Gr
     g = grid.c()
     P = B * N * D * fH * fW
     st = _stream(dev)
-    ws = _plan_workspace(dev, st, shape, g)
-    cells = torch.empty(P, dtype=torch.int32, device=dev)
-    sorted_points = torch.empty(P, dtype=torch.int32, device=dev)
-    sorted_cells = torch.empty(P, dtype=torch.int32, device=dev)
-    cell_range = torch.empty((grid.n_cells(B), 2), dtype=torch.int32, device=dev)
-    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    ws = _workspace(dev, st, _abi.load().lss_plan_workspace_bytes(shape, g))
+    cells, cell_start, sorted_points, sorted_cells, counts = _plan_outputs(P, grid.n_cells(B), dev)
     try:
         _abi.call("lss_build_plan", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
                   _ptr(_f32c(rots)), _ptr(_f32c(trans)), _ptr(_f32c(intrins)),
                   _ptr(_f32c(post_rots)), _ptr(_f32c(post_trans)), g, shape, _ptr(cells),
-                  _ptr(sorted_points), _ptr(sorted_cells), _ptr(cell_range), _ptr(counts), _ptr(ws),
+                  _ptr(cell_start), _ptr(sorted_points), _ptr(sorted_cells), _ptr(counts), _ptr(ws),
                   ws.numel(), st)
     except _abi.LssError:
         ws.zero_()  # a failed call may leave the control words dirty
         raise
-    return Plan(grid, B, N, D, fH, fW, cells, sorted_points, sorted_cells, cell_range, counts)
+    return Plan(grid, B, N, D, fH, fW, cells, cell_start, sorted_points, sorted_cells, counts)
 
 
 def plan_from_geom(geom: torch.Tensor, grid: GridSpec) -> Plan:
     """Plan from a dense (B,N,D,fH,fW,3) geometry tensor (the literal
-    voxel_pooling(geom_feats, x) signature): K1 -> K2 -> K3."""
+    voxel_pooling(geom_feats, x) signature): lss_build_plan_from_geom."""
+    dev = _need_cuda(geom)
     B, N, D, fH, fW, _ = geom.shape
-    q = quantize_rank(geom, grid, B)
-    sk, sp = sort_ranks(q["ranks"], grid.n_cells(B))
-    cell_range, counts, _, sorted_cells = intervals(sk, grid, B)
-    return Plan(grid, B, N, D, fH, fW, q["cells"], sp, sorted_cells, cell_range, counts)
+    geom = _f32c(geom)
+    P = B * N * D * fH * fW
+    g = grid.c()
+    st = _stream(dev)
+    ws = _workspace(dev, st, _abi.load().lss_plan_from_geom_workspace_bytes(P, g, B))
+    cells, cell_start, sorted_points, sorted_cells, counts = _plan_outputs(P, grid.n_cells(B), dev)
+    try:
+        _abi.call("lss_build_plan_from_geom", _ptr(geom), g, B, P, _ptr(cells), _ptr(cell_start),
+                  _ptr(sorted_points), _ptr(sorted_cells), _ptr(counts), _ptr(ws), ws.numel(), st)
+    except _abi.LssError:
+        ws.zero_()
+        raise
+    return Plan(grid, B, N, D, fH, fW, cells, cell_start, sorted_points, sorted_cells, counts)
 
 
 # --------------------------------------------------------------------------
@@ -326,8 +357,8 @@ class _LiftSplat(torch.autograd.Function):
         depth_t, feat_t = lift_stage(depth, feat, plan)
         bev = _alloc_bev(plan, C, dev)
         _abi.call("lss_liftsplat_fwd", _ptr(depth_t), _ptr(feat_t), _ptr(plan.sorted_points),
-                  _ptr(plan.sorted_cells), _ptr(plan.cell_range), _ptr(plan.counts), plan.grid.c(),
-                  plan.shape(C), _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
+                  _ptr(plan.sorted_cells), _ptr(plan.cell_start), plan.grid.c(), plan.shape(C),
+                  _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
         ctx.plan = plan
         ctx.C = C
         ctx.in_dtypes = (depth.dtype, feat.dtype)
@@ -379,8 +410,8 @@ class _PoolDense(torch.autograd.Function):
             raise RuntimeError("x has %d points, plan has %d" % (x2.shape[0], plan.P))
         bev = _alloc_bev(plan, C, dev)
         _abi.call("lss_pool_dense_fwd", _ptr(x2), _ptr(plan.sorted_points), _ptr(plan.sorted_cells),
-                  _ptr(plan.cell_range), _ptr(plan.counts), plan.grid.c(), plan.B, C,
-                  _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
+                  _ptr(plan.cell_start), plan.grid.c(), plan.B, C, plan.P, _abi.LSS_BEV_NHWC, _ptr(bev),
+                  _stream(dev))
         ctx.plan = plan
         ctx.x_shape = tuple(x.shape)
         ctx.x_dtype = x.dtype

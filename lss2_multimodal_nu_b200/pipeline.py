@@ -6,7 +6,7 @@ sequence of a whole forward + backward of the path
 
       +-- lss_lift_stage (side stream) --------+
       |                                        v
-  in -+-- lss_build_plan (K0, K1', K2, K3) ----+--> lss_liftsplat_fwd --> lss_liftsplat_bwd
+  in -+-- lss_build_plan (K0, K1', sort, K3) ----+--> lss_liftsplat_fwd --> lss_liftsplat_bwd
 
 (the staging copies depend only on the features and the plan only on the calibration, so the
 two branches run concurrently inside the graph).  ``run()`` replays the graph on device-resident
@@ -75,8 +75,8 @@ class LiftSplatStep:
         # plan + staging buffers
         self.cells = torch.empty(self.P, **i32)
         self.sorted_points = torch.empty(self.P, **i32)
+        self.cell_start = torch.empty(grid.n_cells(B) + 1, **i32)
         self.sorted_cells = torch.empty(self.P, **i32)
-        self.cell_range = torch.empty((grid.n_cells(B), 2), **i32)
         self.counts = torch.zeros(2, **i32)
         self.depth_t = torch.empty((BN * HW, D), **f32)
         self.feat_t = torch.empty((BN * HW, C), **f32)
@@ -89,7 +89,7 @@ class LiftSplatStep:
         self._stream = stream if stream is not None else torch.cuda.Stream(dev)
         self._side = torch.cuda.Stream(dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
-        self.kernels_per_step = 2 + 1 + 1 + 1      # plan (2 kernels on the single-wave path), stage, fwd, bwd
+        self.kernels_per_step = 4 + 1 + 1 + 1      # plan (cells, scan, scatter, order), stage, fwd, bwd
         # warm run outside capture (module load, function attributes), then capture
         with torch.cuda.stream(self._stream):
             self._enqueue(self._stream, self._side)
@@ -125,14 +125,14 @@ class LiftSplatStep:
         i = self.inputs
         _abi.call("lss_build_plan", p(self.us), p(self.vs), p(self.ds), p(i["rots"]), p(i["trans"]),
                   p(i["intrins"]), p(i["post_rots"]), p(i["post_trans"]), self._g, self._shape,
-                  p(self.cells), p(self.sorted_points), p(self.sorted_cells), p(self.cell_range),
+                  p(self.cells), p(self.cell_start), p(self.sorted_points), p(self.sorted_cells),
                   p(self.counts), p(self._ws), self._ws.numel(), st)
 
     def enqueue_fwd(self, st: int) -> None:
         p = lambda t: t.data_ptr()
         _abi.call("lss_liftsplat_fwd", p(self.depth_t), p(self.feat_t), p(self.sorted_points),
-                  p(self.sorted_cells), p(self.cell_range), p(self.counts), self._g, self._shape,
-                  _abi.LSS_BEV_NHWC, p(self._bev), st)
+                  p(self.sorted_cells), p(self.cell_start), self._g, self._shape, _abi.LSS_BEV_NHWC,
+                  p(self._bev), st)
 
     def enqueue_bwd(self, st: int) -> None:
         p = lambda t: t.data_ptr()
@@ -208,10 +208,6 @@ class HostPipeline:
             block = self.pack(host_inputs, slot["h_in"])
         with torch.cuda.stream(st.stream):
             st.in_block.copy_(block, non_blocking=True)            # one H2D (overlaps the previous step)
-            if self._last_compute is not None:
-                # kernels of consecutive steps do not overlap (the partition kernel wants the GPU
-                # to itself); only the copies do
-                st.stream.wait_event(self._last_compute)
             st.run()
             slot["computed"].record(st.stream)
             self._last_compute = slot["computed"]

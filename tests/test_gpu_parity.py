@@ -64,12 +64,35 @@ def axes_of(g):
 
 
 CAL = ("rots", "trans", "intrins", "post_rots", "post_trans")
+
+
+def cell_major(ref_sorted_points, P, B):
+    """The reference's sort order (by rank, batch digit least significant) regrouped stably by
+    sample: the order a stable sort by output cell gives (see functional.Plan)."""
+    ref = np.asarray(ref_sorted_points)
+    return ref[np.argsort(ref // (P // B), kind="stable")]
+
+
+def check_plan_tables(plan, ref_sorted_points):
+    """cell_start / sorted_points / cells are mutually consistent and carry the reference's order."""
+    K = len(ref_sorted_points)
+    cells = cpu(plan.cells); cs = cpu(plan.cell_start); sp = cpu(plan.sorted_points)[:K]
+    n_cells = plan.grid.n_cells(plan.B)
+    assert cs.shape == (n_cells + 1,) and cs[0] == 0 and cs[-1] == K and (np.diff(cs) >= 0).all()
+    assert (np.bincount(cells[cells >= 0], minlength=n_cells) == np.diff(cs)).all()
+    assert (sp == cell_major(ref_sorted_points, plan.P, plan.B)).all()
+    assert (cells[sp] == np.repeat(np.arange(n_cells), np.diff(cs))).all()
+    sc = cpu(plan.sorted_cells)
+    assert (sc[:K] == cells[sp]).all() and (sc[K:] == -1).all()
+    assert cpu(plan.counts).tolist() == [K, int((np.diff(cs) > 0).sum())]
+
+
 FIXTURES = ["tiny", "edge_none_kept", "edge_one_voxel", "edge_randn_calib", "edge_nonfinite"]
 
 
 def test_library_loaded():
     from lss2_multimodal_nu_b200 import _abi
-    assert _abi.load().lss_abi_version() == 1
+    assert _abi.load().lss_abi_version() == _abi.ABI_VERSION == 2
 
 
 def test_camera_prep_bit_exact(golden_dir):
@@ -156,17 +179,30 @@ def test_fused_plan_matches_stepwise(golden_dir, name):
     g = load(golden_dir, name)
     us, vs, ds = axes_of(g)
     grid = grid_of(g)
+    B = g["trans"].shape[0]
     plan = F.build_plan(us, vs, ds, *(dev(g[k]) for k in CAL), grid)
     step = F.plan_from_geom(dev(g["geom"]), grid)
-    for a in ("cells", "cell_range", "counts"):
+    for a in ("cells", "cell_start", "counts"):
         assert (cpu(getattr(plan, a)) == cpu(getattr(step, a))).all(), a
     K = int(cpu(plan.counts)[0])
+    assert K == len(g["ranks"])
     assert (cpu(plan.sorted_points)[:K] == cpu(step.sorted_points)[:K]).all()
-    assert (cpu(plan.sorted_cells)[:K] == cpu(step.sorted_cells)[:K]).all()
+    # the plan carries the reference's order: stable within every voxel, samples regrouped
+    kept_idx = np.nonzero(g["kept"])[0]
+    check_plan_tables(plan, kept_idx[np.argsort(g["ranks"], kind="stable")])
+    # ... and, through K2 on the reference's ranks, the reference's argsort itself
+    assert (cpu(plan.reference_order()) == kept_idx[np.argsort(g["ranks"], kind="stable")]).all()
+    # the interval table equals what K3 finds on the K2-sorted ranks
+    q = F.quantize_rank(dev(g["geom"]), grid, B)
+    sk, _ = F.sort_ranks(q["ranks"], grid.n_cells(B))
+    cell_range, counts, _, _ = F.intervals(sk, grid, B)
+    cr = cpu(cell_range)
+    assert ((cr[:, 1] - cr[:, 0]) == np.diff(cpu(plan.cell_start))).all()
+    assert cpu(counts).tolist() == cpu(plan.counts).tolist()
     # the workspace is reusable: a second call gives the same plan
     plan2 = F.build_plan(us, vs, ds, *(dev(g[k]) for k in CAL), grid)
     assert (cpu(plan2.sorted_points)[:K] == cpu(plan.sorted_points)[:K]).all()
-    assert (cpu(plan2.cell_range) == cpu(plan.cell_range)).all()
+    assert (cpu(plan2.cell_start) == cpu(plan.cell_start)).all()
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -256,8 +292,9 @@ def test_config1_against_reference_fixture(golden_dir):
     assert (cpu(out["coords"]) == g["coords"]).all()
     assert (cpu(out["ranks"])[kept] == g["ranks"]).all()
     plan = F.build_plan(*axes, *(dev(cal[k]) for k in CAL), grid)
-    K = len(g["ranks"])
-    assert (cpu(plan.sorted_points)[:K] == np.nonzero(kept)[0][g["sorts"]]).all()
+    ref_order = np.nonzero(kept)[0][g["sorts"]]          # the reference's argsort (torch radix path: stable)
+    check_plan_tables(plan, ref_order)
+    assert (cpu(plan.reference_order()) == ref_order).all()
     depth = dev(ft["depth"]).requires_grad_(True); feat = dev(ft["feat"]).requires_grad_(True)
     bev = F.lift_splat(depth, feat, plan)
     pick = tuple(g["bev_pick"].T.astype(np.int64))
@@ -287,10 +324,11 @@ def test_config2_full_size_digests(golden_dir):
     plan = F.build_plan(*axes, *(dev(cal[k]) for k in CAL), grid)
     K, V = cpu(plan.counts).tolist()
     assert (K, V) == (g["K"], g["V"])
-    # sorts[i] = position of sorted_points[i] in the compacted (kept) array
+    # sorts[i] = position of the i-th point of the reference order in the compacted (kept) array
     compact = np.cumsum(kept) - 1
-    sorts = compact[cpu(plan.sorted_points)[:K]].astype(np.int32)
-    assert sha(sorts) == g["sha256"]["sorts_i32"]
+    ref_order = cpu(plan.reference_order())
+    assert sha(compact[ref_order].astype(np.int32)) == g["sha256"]["sorts_i32"]
+    check_plan_tables(plan, ref_order)
     sk, _ = F.sort_ranks(out["ranks"], grid.n_cells(cfg.B))
     _, _, last, _ = F.intervals(sk, grid, cfg.B, want_last_mask=True)
     assert sha(cpu(last)[:K]) == g["sha256"]["last_mask_u8"]
@@ -318,7 +356,7 @@ def test_large_shapes_against_oracle(cname, B):
     plan = F.build_plan(*axes, *(dev(cal[k]) for k in CAL), grid)
     K = len(ip["ranks"])
     assert cpu(plan.counts).tolist() == [K, len(ip["interval_start"])]
-    assert (cpu(plan.sorted_points)[:K] == ip["sorted_point"]).all()
+    check_plan_tables(plan, ip["sorted_point"])
     depth = dev(ft["depth"]).requires_grad_(True); feat = dev(ft["feat"]).requires_grad_(True)
     bev = F.lift_splat(depth, feat, plan)
     bev.backward(dev(dbev))

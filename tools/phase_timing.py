@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Per-phase timeline of the plan kernels (debug build with -DLSS_PHASE_TIMING).
+"""Per-warp timeline of the fused forward kernel (debug build with -DLSS_PHASE_TIMING).
 
-    python tools/phase_timing.py        # builds /tmp/liblss_timing.so, runs config2, prints phase times
+    python tools/phase_timing.py [config2]   # builds gpurun_out/liblss_timing.so, runs the config, prints the timeline
 """
 import ctypes
 import os
@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 src = os.path.join(ROOT, "lss2_multimodal_nu_b200", "csrc")
 so = os.path.join(ROOT, "gpurun_out", "liblss_timing.so")
+os.makedirs(os.path.dirname(so), exist_ok=True)
 subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                 "-shared", "-DLSS_PHASE_TIMING", "-I", os.path.join(ROOT, "include"), "-I", src, "-o", so,
                 os.path.join(src, "lss_abi.cu")], check=True)
@@ -30,28 +31,33 @@ cal = {k: torch.from_numpy(v).to(dev) for k, v in S.make_calibration(cfg).items(
 us, vs, ds = (torch.from_numpy(a).to(dev) for a in O.frustum_axes(cfg.final_dim, cfg.downsample, cfg.dbound))
 grid = F.GridSpec.from_bounds(cfg.xbound, cfg.ybound, cfg.zbound)
 ft = {k: torch.from_numpy(v).to(dev) for k, v in S.make_features(cfg).items()}
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(5):
     plan = F.build_plan(us, vs, ds, cal["rots"], cal["trans"], cal["intrins"], cal["post_rots"], cal["post_trans"], grid)
+    flush.zero_()
     bev = F.lift_splat(ft["depth"], ft["feat"], plan)
 torch.cuda.synchronize()
 lib = _abi.load()
 lib.lss_debug_phase_ts.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
-for kernel, name, nblk in ((0, "partition_coop", (cfg.P + 1023) // 1024), (1, "local_sort", 1024),
-                           (2, "pool_fwd (0-1 FILL warp, 2-6 first REDUCE warp)", 148 * 8)):
-    buf = np.zeros(4096 * 8, np.uint64)
-    lib.lss_debug_phase_ts(kernel, buf.ctypes.data, buf.size)
-    ts = buf.reshape(4096, 8)[:nblk].astype(np.int64)
-    t0 = ts[:, 0].min()
-    rel = (ts - t0) / 1e3
-    print(name, "blocks", nblk)
-    for s in range(8):
-        col = rel[:, s][ts[:, s] > 0]
-        if len(col):
-            print("  stamp %d: min %.2f  median %.2f  max %.2f us  (n=%d)" % (s, col.min(), np.median(col), col.max(), len(col)))
-    if kernel == 0:
-        d = (ts[:, 4] - ts[:, 3]) / 1e3
-        print("  phase B duration by tile: ", " ".join("%.1f" % v for v in d[::8]))
-        d = (ts[:, 7] - ts[:, 6]) / 1e3
-        print("  rank+scatter duration:    ", " ".join("%.1f" % v for v in d[::8]))
-        d = (ts[:, 2] - ts[:, 1]) / 1e3
-        print("  geometry duration:        ", " ".join("%.1f" % v for v in d[::8]))
+n_cells = grid.n_cells(cfg.B)
+fill = min((n_cells + 31) // 32 // 32 + 1, 148 * 2)
+fill = int(os.environ.get("LSS_FILL_CTAS", fill))
+nblk = min(4096, fill + (cfg.P + 255) // 256)
+buf = np.zeros(4096 * 16, np.uint64)
+lib.lss_debug_phase_ts(2, buf.ctypes.data, buf.size)
+ts = buf.reshape(4096, 8, 2)[:nblk].astype(np.int64)
+ok = (ts[:, :, 0] > 0) & (ts[:, :, 1] > 0)
+t0 = ts[:, :, 0][ok].min()
+start = (ts[:, :, 0] - t0) / 1e3
+end = (ts[:, :, 1] - t0) / 1e3
+dur = end - start
+print("pool_fwd: %d CTAs (%d fill); kernel span %.1f us" % (nblk, fill, end[ok].max()))
+for name, sl in (("fill", slice(0, fill)), ("reduce", slice(fill, nblk))):
+    o = ok[sl]
+    print("%-6s warps %5d: start p50 %.1f p90 %.1f max %.1f | duration p50 %.2f p90 %.2f p99 %.2f max %.2f | end p50 %.1f p99 %.1f max %.1f us" % (
+        name, o.sum(), *np.percentile(start[sl][o], [50, 90, 100]), *np.percentile(dur[sl][o], [50, 90, 99, 100]),
+        *np.percentile(end[sl][o], [50, 99, 100])))
+hist, edges = np.histogram(start[ok], bins=12)
+print("  warp starts per %.1f us bin:" % (edges[1] - edges[0]), hist.tolist())
+hist, edges = np.histogram(end[ok], bins=12)
+print("  warp ends   per %.1f us bin:" % (edges[1] - edges[0]), hist.tolist())
