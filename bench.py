@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="config2")
     ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
+    ap.add_argument("--in-flight", type=int, default=0,
+                    help="independent batches in flight (one CUDA stream each); 0: LSS_BENCH_IN_FLIGHT or 4")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 100)")
@@ -198,7 +200,12 @@ def run_ours(args, cfg):
     import lss_oracle as O   # frustum axis tables + cpu_baseline only (never the timed product path)
     us, vs, ds = (torch.from_numpy(a).to(dev) for a in O.frustum_axes(cfg.final_dim, cfg.downsample, cfg.dbound))
     C = cfg.C
-    stream = torch.cuda.Stream(dev)
+    stream = torch.cuda.Stream(dev)                       # timing / per-kernel stream
+    in_flight = args.in_flight or int(os.environ.get("LSS_BENCH_IN_FLIGHT", "4"))
+    in_flight = max(1, min(in_flight, args.sets))
+    # batch set s runs on stream s % in_flight: consecutive batches overlap on the GPU, as independent
+    # micro-batches do in a trainer (the path has no cross-batch dependency)
+    lanes = [torch.cuda.Stream(dev) for _ in range(in_flight)]
     host, steps = [], []
     for s in range(args.sets):
         seed = shard.rank_seed(1234, rank, s)
@@ -206,7 +213,7 @@ def run_ours(args, cfg):
         h = {k: torch.from_numpy(v).pin_memory() for k, v in {**cal, **ft}.items()}
         host.append(h)
         st_ = LiftSplatStep(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, C, grid, us, vs, ds, device=dev,
-                            capture=not args.no_graph, stream=stream)
+                            capture=not args.no_graph, stream=lanes[s % in_flight])
         st_.load(h)
         gen = torch.Generator(device=dev); gen.manual_seed(seed)
         st_._dbev.copy_(torch.randn(st_._dbev.shape, device=dev, generator=gen))
@@ -218,24 +225,32 @@ def run_ours(args, cfg):
         steps[i % len(steps)].run()
 
     def barrier():
-        stream.synchronize()
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(n):
+        """n steps round-robin over the batch sets; CUDA-event time from before the first to after the last."""
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for ln in lanes:
+            ln.wait_stream(stream)
+        for i in range(n):
+            run_step(i)
+        for ln in lanes:
+            stream.wait_stream(ln)
+        e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1)
 
     for i in range(max(3, args.warmup)):
         run_step(i)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        run_step(i)
-    e1.record(stream)
-    stream.synchronize()
+    elapsed_ms = timed(args.steps)
     clocks.stop()
-    elapsed_ms = e0.elapsed_time(e1)
     barrier()
     value = shard.aggregate_throughput(cfg.B * args.steps, elapsed_ms, dev)   # all samples / slowest rank
     elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
@@ -283,28 +298,43 @@ def run_ours(args, cfg):
                 "kernels_us": {k: round(v["mean_us"], 2) for k, v in kt.items()}}
 
     # ---- e2e: HostPipeline (public API), pinned host buffers, two steps in flight ----------
-    e2e_steps = args.e2e_steps or min(args.steps, 200)
+    e2e_steps = args.e2e_steps or min(args.steps, 400)
     pipe = HostPipeline(lambda: LiftSplatStep(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, C, grid, us, vs, ds,
-                                              device=dev, capture=not args.no_graph), depth=2)
+                                              device=dev, capture=not args.no_graph), depth=6)
     for sl in pipe.slots:   # the upstream gradient is produced on the device by the downstream network
         sl["step"]._dbev.copy_(steps[0]._dbev)
     torch.cuda.synchronize()
     checksum = 0.0
-    # the host-side "dataset": one pinned block per batch set, laid out as the step consumes it
-    host_blocks = [pipe.pack(h) for h in host]
+    # the host-side "dataset": every slot's pinned input block holds one batch, laid out as the step
+    # consumes it (a data loader writes there directly); each step copies it to the device
+    host_blocks = [pipe.pack(host[k % len(host)], pipe.input_block(k)) for k in range(len(pipe.slots))]
+
+    dbg = {"sub": 0.0, "col": 0.0}
 
     def e2e_run(n):
         nonlocal checksum
         for i in range(n):
             if pipe.in_flight() == len(pipe.slots):
+                t_ = time.perf_counter()
                 out = pipe.collect()
                 checksum += float(out["d_depth"][0, 0, 0, 0])     # the host really reads the result
-            pipe.submit(host_blocks[i % len(host_blocks)])
+                dbg["col"] += time.perf_counter() - t_
+            t_ = time.perf_counter()
+            pipe.submit()
+            dbg["sub"] += time.perf_counter() - t_
         while pipe.in_flight():
             out = pipe.collect()
             checksum += float(out["d_depth"][0, 0, 0, 0])
 
-    e2e_run(4)
+    e2e_run(40)
+    # the host link this number is bound by: one pinned H2D copy of a step's input block, alone
+    blk = host_blocks[0]; dst = pipe.slots[0]["step"].in_block
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        dst.copy_(blk, non_blocking=True)
+    torch.cuda.synchronize()
+    link = {"h2d_gbs": round(20 * blk.numel() * 4 / (time.perf_counter() - t0) / 1e9, 1)}
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -312,12 +342,17 @@ def run_ours(args, cfg):
     e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    if os.environ.get("LSS_E2E_DEBUG"):
+        sys.stderr.write("e2e host: submit %.1f us, collect %.1f us per step\n" % (
+            dbg["sub"] / (e2e_steps + 40) * 1e6, dbg["col"] / (e2e_steps + 40) * 1e6))
     e2e_value = shard.aggregate_throughput(cfg.B * e2e_steps, e2e_ms, dev)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
            "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
            "note": "pipeline.HostPipeline: pinned host calibration+depth+feat in (one packed H2D), "
-                   "d_depth+d_feat out (one packed D2H), every step's result read on the host, two steps "
-                   "in flight (copies overlap kernels); upstream dBEV stays on the device; host wall clock"}
+                   "d_depth+d_feat out (one packed D2H), both copies inside the slot's CUDA graph, every step's "
+                   "result read on the host, six steps in flight (copies overlap kernels); upstream dBEV "
+                   "stays on the device; host wall clock",
+           "host_link_gbs": link}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -325,6 +360,7 @@ def run_ours(args, cfg):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(cfg), "global_batch": cfg.B * world,
                    "parallelism": "sample-sharded x%d, no collective" % world,
+                   "in_flight": "%d independent batches in flight per GPU (one CUDA stream each)" % in_flight,
                    "bev_layout": "channels_last (NHWC storage of the logical (B,C*Z,X,Y) map)",
                    "l2": "inputs larger than L2: %d rotating batch sets (%.0f MB BEV+dBEV each)"
                          % (args.sets, 2 * alg["bev"] / 1e6),

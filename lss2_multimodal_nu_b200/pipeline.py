@@ -10,8 +10,8 @@ sequence of a whole forward + backward of the path
 
 (the staging copies depend only on the features and the plan only on the calibration, so the
 two branches run concurrently inside the graph).  ``run()`` replays the graph on device-resident
-inputs; ``HostPipeline`` feeds it from pinned HOST buffers with one packed copy per direction and
-keeps two steps in flight, so the copies of step i+1 overlap the kernels of step i.
+inputs; ``HostPipeline`` feeds it from pinned HOST buffers with one packed copy per direction, both
+inside the slot's graph, and keeps several steps in flight, so copies overlap kernels.
 
 Nothing here changes results: it is the sequence functional.build_plan + functional.lift_splat
 (autograd forward and backward) issue, minus the per-call allocations and Python overhead.
@@ -165,29 +165,52 @@ class LiftSplatStep:
 class HostPipeline:
     """Feeds LiftSplatStep objects from pinned host memory, ``depth`` steps in flight.
 
-    submit(host_inputs) packs one step's calibration + depth + feat into a pinned block, issues
-    ONE host->device copy, the captured step, and ONE device->host copy of [d_depth | d_feat];
-    collect() waits for the oldest step in flight and returns its host results.  With two slots
-    the copies of one step overlap the kernels of the other.
+    Every slot owns a pinned input block and a pinned output block and ONE CUDA graph holding the
+    whole round trip: host->device copy of [calibration | depth | feat], the captured step, and
+    the device->host copy of [d_depth | d_feat].  A data loader writes a batch straight into
+    ``input_block(k)`` (laid out by ``pack``), ``submit()`` replays the slot's graph and
+    ``collect()`` waits for the oldest step in flight and returns its host results.  With several
+    slots the copies of one step overlap the kernels of the others (each slot has its own stream).
+    ``submit(host_inputs)`` first packs / copies the given tensors into the slot's block (host
+    memcpy; convenient, slower).
     """
 
-    def __init__(self, make_step, depth: int = 2):
+    def __init__(self, make_step, depth: int = 2, graph_io: bool = True):
         self.slots = []
         for _ in range(depth):
             st: LiftSplatStep = make_step()
             h_in = torch.empty(st.in_block.numel(), dtype=torch.float32).pin_memory()
             h_out = torch.empty(st.out_block.numel(), dtype=torch.float32).pin_memory()
-            self.slots.append({"step": st, "h_in": h_in, "h_out": h_out,
-                               "done": torch.cuda.Event(), "computed": torch.cuda.Event(), "busy": False})
+            slot = {"step": st, "h_in": h_in, "h_out": h_out, "done": torch.cuda.Event(), "busy": False,
+                    "graph": None}
+            self.slots.append(slot)
+            self._round_trip(slot)                       # warm run outside capture
+            st.stream.synchronize()
+            if st._graph is not None and graph_io:       # the step itself is graph-captured: capture the I/O too
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st.stream):
+                    self._round_trip(slot, capturing=True)
+                slot["graph"] = g
         self._next, self._oldest = 0, 0
-        self._last_compute: Optional[torch.cuda.Event] = None
         s0 = self.slots[0]["step"]
         self.h2d_bytes = s0.in_block.numel() * 4
         self.d2h_bytes = s0.out_block.numel() * 4
 
+    @staticmethod
+    def _round_trip(slot, capturing: bool = False) -> None:
+        st: LiftSplatStep = slot["step"]
+        stream = torch.cuda.current_stream(st.dev) if capturing else st.stream
+        with torch.cuda.stream(stream):
+            st.in_block.copy_(slot["h_in"], non_blocking=True)         # one H2D
+            st._enqueue(stream, st._side)
+            slot["h_out"].copy_(st.out_block, non_blocking=True)       # one D2H
+
+    def input_block(self, k: int) -> torch.Tensor:
+        """Pinned input block of slot k (layout: LiftSplatStep.in_block, see pack())."""
+        return self.slots[k]["h_in"]
+
     def pack(self, host_inputs: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Pack one step's inputs into a pinned block laid out like LiftSplatStep.in_block (a data
-        loader can also write straight into such a block and skip this copy)."""
+        """Pack one step's inputs into a pinned block laid out like LiftSplatStep.in_block."""
         st: LiftSplatStep = self.slots[0]["step"]
         if out is None:
             out = torch.empty(st.in_block.numel(), dtype=torch.float32).pin_memory()
@@ -195,26 +218,34 @@ class HostPipeline:
             out[o:o + n].copy_(host_inputs[k].reshape(-1))
         return out
 
-    def submit(self, host_inputs) -> None:
-        """host_inputs: a dict of host tensors (rots, trans, intrins, post_rots, post_trans, depth,
-        feat) or one pre-packed pinned block from pack()."""
-        slot = self.slots[self._next]
+    def submit(self, host_inputs=None) -> int:
+        """Start one step on the next free slot and return the slot index.  ``host_inputs``: None
+        (the slot's input block was filled in place), a dict of host tensors (rots, trans, intrins,
+        post_rots, post_trans, depth, feat) or one block from pack()."""
+        k = self._next
+        slot = self.slots[k]
         if slot["busy"]:
             raise RuntimeError("pipeline full: collect() first")
         st: LiftSplatStep = slot["step"]
         if isinstance(host_inputs, torch.Tensor):
-            block = host_inputs
+            if host_inputs.data_ptr() != slot["h_in"].data_ptr():
+                slot["h_in"].copy_(host_inputs)
+        elif host_inputs is not None:
+            self.pack(host_inputs, slot["h_in"])
+        if slot["graph"] is not None:
+            with torch.cuda.stream(st.stream):
+                slot["graph"].replay()
+        elif st._graph is not None:
+            with torch.cuda.stream(st.stream):
+                st.in_block.copy_(slot["h_in"], non_blocking=True)
+                st._graph.replay()
+                slot["h_out"].copy_(st.out_block, non_blocking=True)
         else:
-            block = self.pack(host_inputs, slot["h_in"])
-        with torch.cuda.stream(st.stream):
-            st.in_block.copy_(block, non_blocking=True)            # one H2D (overlaps the previous step)
-            st.run()
-            slot["computed"].record(st.stream)
-            self._last_compute = slot["computed"]
-            slot["h_out"].copy_(st.out_block, non_blocking=True)   # one D2H
-            slot["done"].record(st.stream)
+            self._round_trip(slot)
+        slot["done"].record(st.stream)
         slot["busy"] = True
-        self._next = (self._next + 1) % len(self.slots)
+        self._next = (k + 1) % len(self.slots)
+        return k
 
     def collect(self) -> Dict[str, torch.Tensor]:
         slot = self.slots[self._oldest]

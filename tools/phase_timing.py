@@ -40,9 +40,9 @@ torch.cuda.synchronize()
 lib = _abi.load()
 lib.lss_debug_phase_ts.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
 n_cells = grid.n_cells(cfg.B)
-fill = min((n_cells + 31) // 32 // 32 + 1, 148 * 2)
+fill = min(((n_cells + 31) // 32 + 7) // 8, 148)
 fill = int(os.environ.get("LSS_FILL_CTAS", fill))
-nblk = min(4096, fill + (cfg.P + 255) // 256)
+rows = min(40, 8704 // (cfg.C * 4)); chunk = min(32, rows - min(8, rows // 4)); nblk = min(4096, fill + (cfg.P + chunk * 8 - 1) // (chunk * 8))
 buf = np.zeros(4096 * 16, np.uint64)
 lib.lss_debug_phase_ts(2, buf.ctypes.data, buf.size)
 ts = buf.reshape(4096, 8, 2)[:nblk].astype(np.int64)
@@ -54,6 +54,8 @@ dur = end - start
 print("pool_fwd: %d CTAs (%d fill); kernel span %.1f us" % (nblk, fill, end[ok].max()))
 for name, sl in (("fill", slice(0, fill)), ("reduce", slice(fill, nblk))):
     o = ok[sl]
+    if not o.any():
+        continue
     print("%-6s warps %5d: start p50 %.1f p90 %.1f max %.1f | duration p50 %.2f p90 %.2f p99 %.2f max %.2f | end p50 %.1f p99 %.1f max %.1f us" % (
         name, o.sum(), *np.percentile(start[sl][o], [50, 90, 100]), *np.percentile(dur[sl][o], [50, 90, 99, 100]),
         *np.percentile(end[sl][o], [50, 99, 100])))
