@@ -150,16 +150,21 @@ int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid,
  * interval detection of src/tools.py:196-197.  The plan depends only on the
  * calibration, so evaluation code can build it once per rig and reuse it.
  *
- * The sort key is the OUTPUT CELL ((b*X + x)*Y + y)*Z + z -- the reference's
- * rank with its batch digit moved to the front, a bijection of the rank -- and
- * the sort is stable, so each voxel's run holds the reference's points in the
- * reference's order; runs follow one another sample-major instead of
- * sample-minor.  (lss_sort_ranks is the bit-exact argsort of the rank itself.)
- *   d_cells         (P)          output cell of every point, -1 if it fails the bounds test
- *   d_cell_start    (n_cells+1)  cell c owns d_sorted_points[d_cell_start[c] .. d_cell_start[c+1]);
- *                                equal bounds = empty voxel; d_cell_start[n_cells] = K.
+ * The sort key is the OUTPUT CELL in tile-major order: the BEV plane of every
+ * sample is cut into T x T tiles (T = lss_plan_key_tile() = 8) and
+ *   key = ((((b*XT + x/T)*YT + y/T)*T + x%T)*T + y%T)*Z + z,  XT = ceil(X/T), YT = ceil(Y/T)
+ * -- the digits of the reference's rank x*(Y*Z*B) + y*(Z*B) + z*B + b regrouped, a
+ * bijection of the rank on the existing cells -- and the sort is stable, so each
+ * voxel's run holds the reference's points in the reference's order; only the
+ * order in which runs follow one another differs (neighbours in the list are
+ * neighbours on the map).  lss_sort_ranks is the bit-exact argsort of the rank itself.
+ * n_keys = lss_plan_key_count(grid, B) = B*XT*YT*T*T*Z >= n_cells.
+ *   d_cells         (P)          output cell ((b*X + x)*Y + y)*Z + z of every point, -1 if it
+ *                                fails the bounds test
+ *   d_key_start     (n_keys+1)   key k owns d_sorted_points[d_key_start[k] .. d_key_start[k+1]);
+ *                                equal bounds = empty voxel; d_key_start[n_keys] = K.
  *                                This table is the interval detection (K3).
- *   d_sorted_points (P)          point ids ordered by (cell, point id); first K entries valid
+ *   d_sorted_points (P)          point ids ordered by (key, point id); first K entries valid
  *   d_sorted_cells  (P)          output cell of each sorted point; -1 beyond the K kept points
  *   d_counts        (2)          {K kept points, V occupied voxels}
  *   workspace: lss_plan_workspace_bytes(shape, grid) bytes, 16-byte aligned, ZERO-FILLED
@@ -168,15 +173,17 @@ int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid,
  * (P,3) (the literal voxel_pooling(geom_feats, x) signature, src/model_baseline.py:84).
  * ------------------------------------------------------------------------- */
 size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid);
+int64_t lss_plan_key_count(const LssGrid* grid, int32_t B);
+int lss_plan_key_tile(void);
 int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
                    const float* d_trans, const float* d_intrins, const float* d_post_rots,
                    const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
-                   int32_t* d_cells, int32_t* d_cell_start, int32_t* d_sorted_points,
+                   int32_t* d_cells, int32_t* d_key_start, int32_t* d_sorted_points,
                    int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace, size_t workspace_bytes,
                    void* stream);
 size_t lss_plan_from_geom_workspace_bytes(int64_t P, const LssGrid* grid, int32_t B);
 int lss_build_plan_from_geom(const float* d_geom, const LssGrid* grid, int32_t B, int64_t P,
-                             int32_t* d_cells, int32_t* d_cell_start, int32_t* d_sorted_points,
+                             int32_t* d_cells, int32_t* d_key_start, int32_t* d_sorted_points,
                              int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace,
                              size_t workspace_bytes, void* stream);
 
@@ -190,7 +197,7 @@ int lss_build_plan_from_geom(const float* d_geom, const LssGrid* grid, int32_t B
  *     d_dx[p,:] = d_dbev[cell(p),:] for kept points, 0 otherwise.
  * ------------------------------------------------------------------------- */
 int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
-                       const int32_t* d_cell_start, const LssGrid* grid, int32_t B, int32_t C, int64_t P,
+                       const int32_t* d_key_start, const LssGrid* grid, int32_t B, int32_t C, int64_t P,
                        int32_t layout, float* d_bev, void* stream);
 int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGrid* grid,
                        int32_t B, int32_t C, int64_t P, int32_t layout, float* d_dx,
@@ -217,7 +224,7 @@ int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* sh
  *     gather, as QuickCumsum.backward is); points that were dropped contribute 0.
  * ------------------------------------------------------------------------- */
 int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32_t* d_sorted_points,
-                      const int32_t* d_sorted_cells, const int32_t* d_cell_start, const LssGrid* grid,
+                      const int32_t* d_sorted_cells, const int32_t* d_key_start, const LssGrid* grid,
                       const LssShape* shape, int32_t layout, float* d_bev, void* stream);
 int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
                       const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,

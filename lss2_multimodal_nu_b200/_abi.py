@@ -57,6 +57,8 @@ SIGNATURES = {
     "lss_liftsplat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _G, _S, _i32, _p, _p]),
     "lss_liftsplat_bwd": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _p, _p, _p]),
     "lss_plan_workspace_bytes": (_sz, [_S, _G]),
+    "lss_plan_key_count": (_i64, [_G, _i32]),
+    "lss_plan_key_tile": (C.c_int, []),
     "lss_build_plan": (C.c_int, [_p] * 8 + [_G, _S, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "lss_plan_from_geom_workspace_bytes": (_sz, [_i64, _G, _i32]),
     "lss_build_plan_from_geom": (C.c_int, [_p, _G, _i32, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -69,7 +69,10 @@ static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& 
                     long long points_per_sample, int32_t* d_cells, int32_t* d_cell_start,
                     int32_t* d_sorted_points, int32_t* d_sorted_cells, int32_t* d_counts, void* ws,
                     size_t ws_bytes, cudaStream_t st) {
-  const PlanWorkspace pw = make_plan_workspace(P, g.n_cells);
+  KeyMap km;
+  int rck = make_keymap(g, &km);
+  if (rck) return rck;
+  const PlanWorkspace pw = make_plan_workspace(P, km.n_keys);
   LSS_REQUIRE(ws_bytes >= pw.total_bytes, LSS_ERR_WORKSPACE_TOO_SMALL);
   LSS_REQUIRE(aligned16(ws) && aligned16(d_cell_start), LSS_ERR_MISALIGNED);
   char* w = static_cast<char*>(ws);
@@ -81,7 +84,7 @@ static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& 
 
   PlanCellsArgs ca;
   memset(&ca, 0, sizeof(ca));
-  ca.grid = g; ca.P = P; ca.cells = d_cells; ca.cnt = cnt; ca.counts = d_counts; ca.ctl = ctl;
+  ca.grid = g; ca.keys = km; ca.P = P; ca.cells = d_cells; ca.cnt = cnt; ca.counts = d_counts; ca.ctl = ctl;
   const unsigned tiles = (unsigned)((P + kPlanTile - 1) / kPlanTile);
   if (ga) {
     ca.geom = *ga;
@@ -98,13 +101,13 @@ static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& 
   LSS_LAUNCH_CHECK("plan_cells_kernel");
 
   PlanScanArgs sa;
-  sa.cnt = cnt; sa.n = g.n_cells; sa.tiles = pw.scan_tiles; sa.cell_start = d_cell_start;
+  sa.cnt = cnt; sa.n = km.n_keys; sa.tiles = pw.scan_tiles; sa.cell_start = d_cell_start;
   sa.state = state; sa.ctl = ctl; sa.counts = d_counts; sa.long_list = long_list;
   plan_scan_kernel<<<(unsigned)pw.scan_tiles, kPlanThreads, 0, st>>>(sa);
   LSS_LAUNCH_CHECK("plan_scan_kernel");
 
   PlanScatterArgs sc;
-  sc.cells = d_cells; sc.P = P; sc.cnt = cnt; sc.cell_start = d_cell_start;
+  sc.cells = d_cells; sc.P = P; sc.keys = km; sc.cnt = cnt; sc.cell_start = d_cell_start;
   sc.tmp_pt = tmp_pt; sc.sorted_cells = d_sorted_cells; sc.state = state; sc.scan_tiles = pw.scan_tiles; sc.ctl = ctl;
   long long blocks = (P + kPlanThreads - 1) / kPlanThreads;
   const long long cap = (long long)sm_count() * 16;
@@ -113,7 +116,7 @@ static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& 
   LSS_LAUNCH_CHECK("plan_scatter_kernel");
 
   PlanOrderArgs oa;
-  oa.tmp_pt = tmp_pt; oa.sorted_cells = d_sorted_cells; oa.cell_start = d_cell_start; oa.n_cells = g.n_cells;
+  oa.tmp_pt = tmp_pt; oa.sorted_cells = d_sorted_cells; oa.cell_start = d_cell_start; oa.keys = km; oa.n_cells = km.n_keys;
   oa.P = P; oa.sorted_points = d_sorted_points; oa.ctl = ctl; oa.long_list = long_list;
   plan_order_kernel<<<(unsigned)blocks, kPlanThreads, 0, st>>>(oa);
   LSS_LAUNCH_CHECK("plan_order_kernel");
@@ -269,13 +272,15 @@ static int pool_fwd_common(bool fused, const float* d_depth_t, const float* d_fe
   memset(&a, 0, sizeof(a));
   a.depth_t = d_depth_t; a.feat_t = d_feat_t; a.x = d_x;
   a.sorted_points = d_sorted_points; a.sorted_cells = d_sorted_cells; a.cell_start = d_cell_start;
-  a.bev = d_bev; a.P = P; a.n_cells = g.n_cells;
+  a.bev = d_bev; a.P = P;
+  rc = make_keymap(g, &a.keys);
+  if (rc) return rc;
   a.C = C; a.D = D; a.HW = HW;
   a.div_dhw = FastDiv((uint32_t)(dhw > 0 ? dhw : 1)); a.div_hw = FastDiv((uint32_t)(HW > 0 ? HW : 1));
   a.div_g4 = FastDiv((uint32_t)(C / 4));
   // fill CTAs: one per SM by default, so the zero stream runs in the background for the whole kernel
   long long fill = sm_count();
-  const long long fill_blocks = ((long long)g.n_cells + 31) / 32;
+  const long long fill_blocks = ((long long)a.keys.n_keys + 31) / 32;
   if (fill * kPoolWarps > fill_blocks) fill = (fill_blocks + kPoolWarps - 1) / kPoolWarps;
   if (const char* e = getenv("LSS_FILL_CTAS")) fill = atoi(e);   // tuning knob
   if (fill < 1) fill = 1;
@@ -379,8 +384,19 @@ size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid) {
   if (check_shape(shape) != LSS_OK) return 0;
   GridDev g;
   if (make_grid(grid, shape->B, &g) != LSS_OK) return 0;
-  return make_plan_workspace(shape_points(shape), g.n_cells).total_bytes;
+  KeyMap km;
+  if (make_keymap(g, &km) != LSS_OK) return 0;
+  return make_plan_workspace(shape_points(shape), km.n_keys).total_bytes;
 }
+
+int64_t lss_plan_key_count(const LssGrid* grid, int32_t B) {
+  GridDev g;
+  KeyMap km;
+  if (make_grid(grid, B, &g) != LSS_OK || make_keymap(g, &km) != LSS_OK) return 0;
+  return km.n_keys;
+}
+
+int lss_plan_key_tile(void) { return kKeyTile; }
 
 int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
                    const float* d_trans, const float* d_intrins, const float* d_post_rots,
@@ -423,8 +439,9 @@ int lss_build_plan_from_geom(const float* d_geom, const LssGrid* grid, int32_t B
 
 size_t lss_plan_from_geom_workspace_bytes(int64_t P, const LssGrid* grid, int32_t B) {
   GridDev g;
-  if (P <= 0 || P >= (1ll << 30) || make_grid(grid, B, &g) != LSS_OK) return 0;
-  return make_plan_workspace(P, g.n_cells).total_bytes;
+  KeyMap km;
+  if (P <= 0 || P >= (1ll << 30) || make_grid(grid, B, &g) != LSS_OK || make_keymap(g, &km) != LSS_OK) return 0;
+  return make_plan_workspace(P, km.n_keys).total_bytes;
 }
 
 #ifdef LSS_PHASE_TIMING

@@ -107,6 +107,53 @@ inline int make_grid(const LssGrid* g, int32_t B, GridDev* out) {
   return LSS_OK;
 }
 
+// ---- the plan's sort key ----------------------------------------------------
+// Output cells are sorted in TILE-major order: the BEV plane of every sample is cut into T x T
+// tiles (T = kKeyTile) and key = ((((b*XT + xt)*YT + yt)*T + xi)*T + yi)*Z + z.  Points that are
+// neighbours in the sorted list then fall into the same few square metres of the map, i.e. they
+// come from the same few camera rays, and the feature rows they gather are re-used out of L1.
+// The key is a bijection of the reference's rank on the cells that exist (n_keys >= n_cells:
+// when X or Y is no multiple of T the last tiles hold keys without a cell, which never occur).
+constexpr int kKeyTile = 8;
+
+struct KeyMap {
+  int32_t X, Y, Z, XT, YT, n_keys;
+  FastDiv div_z, div_y, div_x;        // cell -> (b, x, y, z)
+  FastDiv div_tz, div_yt, div_xt;     // key  -> (b, xt, yt, xi, yi, z)
+  __host__ __device__ __forceinline__ uint32_t key_of_cell(uint32_t cell) const {
+    uint32_t t, z, t2, y, b, x;
+    div_z.divmod(cell, t, z);
+    div_y.divmod(t, t2, y);
+    div_x.divmod(t2, b, x);
+    const uint32_t xt = x / kKeyTile, xi = x % kKeyTile, yt = y / kKeyTile, yi = y % kKeyTile;
+    return ((((b * XT + xt) * YT + yt) * kKeyTile + xi) * kKeyTile + yi) * Z + z;
+  }
+  // output cell of a key, or -1 when the key has no cell (x >= X or y >= Y in the last tiles)
+  __host__ __device__ __forceinline__ int32_t cell_of_key(uint32_t key) const {
+    uint32_t t, z, tile, in, t2, yt, b, xt;
+    div_z.divmod(key, t, z);
+    div_tz.divmod(t, tile, in);                        // in = xi*T + yi
+    div_yt.divmod(tile, t2, yt);
+    div_xt.divmod(t2, b, xt);
+    const uint32_t x = xt * kKeyTile + in / kKeyTile, y = yt * kKeyTile + in % kKeyTile;
+    if (x >= static_cast<uint32_t>(X) || y >= static_cast<uint32_t>(Y)) return -1;
+    return static_cast<int32_t>(((b * X + x) * Y + y) * Z + z);
+  }
+};
+
+inline int make_keymap(const GridDev& g, KeyMap* k) {
+  k->X = g.nx[0]; k->Y = g.nx[1]; k->Z = g.nx[2];
+  k->XT = (g.nx[0] + kKeyTile - 1) / kKeyTile;
+  k->YT = (g.nx[1] + kKeyTile - 1) / kKeyTile;
+  const long long n = (long long)g.B * k->XT * k->YT * kKeyTile * kKeyTile * k->Z;
+  if (n >= 0x7fffffffLL) return LSS_ERR_BAD_DIMENSION;
+  k->n_keys = static_cast<int32_t>(n);
+  k->div_z = FastDiv((uint32_t)k->Z); k->div_y = FastDiv((uint32_t)k->Y); k->div_x = FastDiv((uint32_t)k->X);
+  k->div_tz = FastDiv((uint32_t)(kKeyTile * kKeyTile)); k->div_yt = FastDiv((uint32_t)k->YT);
+  k->div_xt = FastDiv((uint32_t)k->XT);
+  return LSS_OK;
+}
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // Optional phase timestamps (build with -DLSS_PHASE_TIMING; tools/phase_timing.py reads them).

@@ -16,12 +16,12 @@
 //               order a STABLE sort gives (argsort on torch's radix path): each
 //               point counts the smaller ids in its run.  Runs longer than
 //               kPlanLongRun (adversarial inputs) are bitonic-sorted by one CTA.
-// The key is the OUTPUT CELL ((b*X + x)*Y + y)*Z + z, i.e. the reference's rank
-// x*(Y*Z*B) + y*(Z*B) + z*B + b with the batch digit moved to the front: a
-// bijection of the rank, so runs, per-run order and therefore every per-voxel sum
-// are the reference's; only the order in which the runs follow one another
-// differs (sample-major), which is what makes a run's output line, its
-// neighbours' lines and the feature rows they gather from adjacent in memory.
+// The key is the OUTPUT CELL in tile-major order (KeyMap, lss_common.cuh): the
+// digits (b, x, y, z) of the reference's rank x*(Y*Z*B) + y*(Z*B) + z*B + b
+// regrouped as (b, x/8, y/8, x%8, y%8, z) -- a bijection of the rank, so runs,
+// per-run order and therefore every per-voxel sum are the reference's; only the
+// order in which the runs follow one another differs, which is what makes
+// neighbours in the sorted list neighbours on the map (and in L1).
 // lss_sort_ranks (K2) remains the bit-exact argsort of the reference's rank.
 #pragma once
 
@@ -44,11 +44,11 @@ struct PlanWorkspace {
   int scan_tiles;
 };
 
-inline PlanWorkspace make_plan_workspace(long long P, int32_t n_cells) {
+inline PlanWorkspace make_plan_workspace(long long P, int32_t n_keys) {
   PlanWorkspace w;
   size_t off = 0;
-  w.scan_tiles = (int)(((long long)n_cells + kScanTile - 1) / kScanTile);
-  w.off_cnt = off; off += align_up((size_t)n_cells * 4, 256);        // zero between calls
+  w.scan_tiles = (int)(((long long)n_keys + kScanTile - 1) / kScanTile);
+  w.off_cnt = off; off += align_up((size_t)n_keys * 4, 256);        // zero between calls
   w.off_state = off; off += align_up((size_t)w.scan_tiles * 4, 256); // zero between calls
   w.off_ctl = off; off += 256;                                       // [0] ticket (zero between calls), [1] n_long
   w.off_tmp_pt = off; off += align_up((size_t)P * 4, 256);
@@ -66,10 +66,11 @@ struct PlanCellsArgs {
   GeomArgs geom;            // raw calibration + frustum axes (fused variant)
   const float* dense_geom;  // (P,3) (dense variant)
   GridDev grid;
+  KeyMap keys;
   FastDiv div_ppc, div_hw, div_w, div_n, div_pps;
   long long P;
   int32_t* cells;           // (P)
-  uint32_t* cnt;            // (n_cells) zero on entry
+  uint32_t* cnt;            // (n_keys) zero on entry
   int32_t* counts;          // {K, V}: cleared here
   uint32_t* ctl;            // ctl[1] = n_long: cleared here
 };
@@ -155,7 +156,7 @@ plan_cells_kernel(PlanCellsArgs a) {
     }
     int32_t cell;
     quantize_point_core(gx, gy, gz, b, a.grid, p, out, &cell);
-    if (cell >= 0) atomicAdd(a.cnt + cell, 1u);   // result unused: RED.ADD
+    if (cell >= 0) atomicAdd(a.cnt + a.keys.key_of_cell(static_cast<uint32_t>(cell)), 1u);   // result unused: RED.ADD
   }
 }
 
@@ -166,10 +167,10 @@ plan_cells_kernel(PlanCellsArgs a) {
 // their predecessors 32 at a time.  By-products: K, V and the list of long runs.
 // ---------------------------------------------------------------------------
 struct PlanScanArgs {
-  const uint32_t* cnt;   // (n) per-cell counts
-  int n;                 // n_cells
+  const uint32_t* cnt;   // (n) per-key counts
+  int n;                 // n_keys
   int tiles;
-  int32_t* cell_start;   // (n + 1)
+  int32_t* cell_start;   // (n + 1) key_start
   uint32_t* state;       // [tiles] zero on entry
   uint32_t* ctl;         // [0] ticket (zero on entry), [1] n_long
   int32_t* counts;       // {K, V}, zero on entry
@@ -292,8 +293,9 @@ plan_scan_kernel(PlanScanArgs a) {
 struct PlanScatterArgs {
   const int32_t* cells;
   long long P;
+  KeyMap keys;
   uint32_t* cnt;
-  const int32_t* cell_start;
+  const int32_t* cell_start;   // key_start
   int32_t* tmp_pt;
   int32_t* sorted_cells;   // output cell of each slot (final: the order inside a run does not change it)
   uint32_t* state;   // scan status words: wiped for the next call
@@ -311,8 +313,9 @@ plan_scatter_kernel(PlanScatterArgs a) {
   for (long long p = (long long)blockIdx.x * kPlanThreads + threadIdx.x; p < a.P; p += stride) {
     const int32_t c = __ldg(a.cells + p);
     if (c >= 0) {
-      const uint32_t slot = atomicSub(a.cnt + c, 1u) - 1u;
-      const int32_t pos = __ldg(a.cell_start + c) + static_cast<int32_t>(slot);
+      const uint32_t key = a.keys.key_of_cell(static_cast<uint32_t>(c));
+      const uint32_t slot = atomicSub(a.cnt + key, 1u) - 1u;
+      const int32_t pos = __ldg(a.cell_start + key) + static_cast<int32_t>(slot);
       a.tmp_pt[pos] = static_cast<int32_t>(p);
       a.sorted_cells[pos] = c;
     }
@@ -325,8 +328,9 @@ plan_scatter_kernel(PlanScatterArgs a) {
 struct PlanOrderArgs {
   const int32_t* tmp_pt;
   int32_t* sorted_cells;      // [K, P) is set to -1 here
-  const int32_t* cell_start;
-  int n_cells;
+  const int32_t* cell_start;  // key_start
+  KeyMap keys;
+  int n_cells;                // n_keys
   long long P;
   int32_t* sorted_points;
   const uint32_t* ctl;        // [1] n_long
@@ -345,7 +349,7 @@ plan_order_kernel(PlanOrderArgs a) {
   for (long long i = (long long)blockIdx.x * kPlanThreads + threadIdx.x; i < a.P; i += stride) {
     if (i >= K) { a.sorted_cells[i] = -1; continue; }
     const int32_t p = __ldg(a.tmp_pt + i);
-    const int32_t c = a.sorted_cells[i];
+    const uint32_t c = a.keys.key_of_cell(static_cast<uint32_t>(a.sorted_cells[i]));
     const int s = __ldg(a.cell_start + c), e = __ldg(a.cell_start + c + 1);
     if (e - s <= kPlanLongRun) {
       int rank = 0;

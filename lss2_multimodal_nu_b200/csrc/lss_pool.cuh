@@ -110,8 +110,9 @@ lift_stage_kernel(const float* __restrict__ depth, const float* __restrict__ fea
 // K4 / K4a forward, channels-innermost BEV.
 //
 // The BEV map is (cell, C) with cell = ((b*X + x)*Y + y)*Z + z, one voxel = one
-// contiguous line, and the plan's point list is sorted by cell, so cell c owns
-// sorted_points[cell_start[c] .. cell_start[c+1]).  Every output element is
+// contiguous line, and the plan's point list is sorted by the cell's tile-major
+// key (KeyMap), so key k owns sorted_points[key_start[k] .. key_start[k+1]) and
+// neighbours in the list are neighbours on the map.  Every output element is
 // written exactly once (this is the torch.zeros + index_put + cat of reference
 // src/model_baseline.py:120-124) by two kinds of CTAs that run side by side:
 //   * FILL CTAs stream zeros into the empty voxels (75 % of the map at the
@@ -139,10 +140,10 @@ struct PoolFwdArgs {
   const float* x;                 // (P, C)       dense
   const int32_t* sorted_points;   // (P) sorted by output cell, ascending point id inside a cell
   const int32_t* sorted_cells;    // (P) output cell of each sorted point, -1 beyond the K kept points
-  const int32_t* cell_start;      // (n_cells + 1)
+  const int32_t* cell_start;      // (n_keys + 1) interval bounds, indexed by key
   float* bev;                     // (n_cells, C)
   long long P;
-  int n_cells;
+  KeyMap keys;
   int fill_ctas;                  // CTAs [0, fill_ctas) zero-fill, the rest reduce
   int C, D, HW;
   FastDiv div_dhw, div_hw, div_g4;
@@ -181,17 +182,20 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
   if (lane == 0) phase_stamp_any(2, warp * 2);
 
   // ======================= FILL: zeros into the empty voxels ==========================
+  // A warp takes 32 consecutive KEYS (tile-major order, KeyMap): their interval bounds are one
+  // coalesced load; every group of 8 keys is 8 consecutive voxels of one tile row, i.e. one
+  // contiguous piece of the map, covered with 128-bit stores wherever the voxel is empty.
   if (static_cast<int>(blockIdx.x) < a.fill_ctas) {
-    const int n_blocks = (a.n_cells + 31) >> 5;
+    const int n_blocks = (a.keys.n_keys + 31) >> 5;
     const int stride = a.fill_ctas * kPoolWarps;
     const int G4 = a.C >> 2;                                 // float4 per line
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     int blk = blockIdx.x * kPoolWarps + warp;
     if (blk >= n_blocks) return;
     auto bounds = [&](int bk, int& lo, int& hi) {
-      const int c = (bk << 5) + lane;
-      lo = 0; hi = 1;                                        // beyond the map: not ours to write
-      if (c < a.n_cells) { lo = __ldg(a.cell_start + c); hi = __ldg(a.cell_start + c + 1); }
+      const int k = (bk << 5) + lane;
+      lo = 0; hi = 1;                                        // beyond the key space: not ours to write
+      if (k < a.keys.n_keys) { lo = __ldg(a.cell_start + k); hi = __ldg(a.cell_start + k + 1); }
     };
     int lo, hi;
     bounds(blk, lo, hi);
@@ -199,16 +203,24 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
       const int nxt = blk + stride;
       int nlo = 0, nhi = 1;
       if (nxt < n_blocks) bounds(nxt, nlo, nhi);             // prefetch before the stores go out
-      const uint32_t empty = __ballot_sync(0xffffffffu, hi == lo);
+      const int k = (blk << 5) + lane;
+      const int mycell = (k < a.keys.n_keys) ? a.keys.cell_of_key(static_cast<uint32_t>(k)) : -1;
+      const uint32_t empty = __ballot_sync(0xffffffffu, mycell >= 0 && hi == lo);
       if (empty) {
-        float4* dst = reinterpret_cast<float4*>(a.bev + (size_t)(blk << 5) * a.C);
-        const int n4 = 32 * G4;
-        if (empty == 0xffffffffu) {
-          for (int e = lane; e < n4; e += 32) dst[e] = z4;
-        } else {
-          for (int e = lane; e < n4; e += 32) {
-            const uint32_t line = a.div_g4.div(static_cast<uint32_t>(e));
-            if ((empty >> line) & 1u) dst[e] = z4;
+        const int n4 = 8 * G4;                               // float4 per group of 8 voxels
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t em = (empty >> (8 * g)) & 0xffu;
+          const int base = __shfl_sync(0xffffffffu, mycell, 8 * g);
+          if (em == 0u) continue;
+          float4* dst = reinterpret_cast<float4*>(a.bev + (size_t)base * a.C);
+          if (em == 0xffu) {
+            for (int e = lane; e < n4; e += 32) dst[e] = z4;
+          } else {
+            for (int e = lane; e < n4; e += 32) {
+              const uint32_t line = a.div_g4.div(static_cast<uint32_t>(e));
+              if ((em >> line) & 1u) dst[e] = z4;
+            }
           }
         }
       }

@@ -202,9 +202,11 @@ def intervals(sorted_ranks: torch.Tensor, grid: GridSpec, B: int, want_last_mask
 class Plan:
     """Per-batch index tables: depends on calibration + grid only, never on features.
 
-    The point list is sorted by OUTPUT CELL ((b*X + x)*Y + y)*Z + z -- the reference's rank
-    (src/model_baseline.py:106-109) with the batch digit moved to the front -- stably, so every
-    voxel's run holds the reference's points in the reference's order (see reference_order())."""
+    The point list is sorted stably by the output cell's TILE-MAJOR key (keys_of_cells below;
+    include/lss_b200.h): the digits (b, x, y, z) of the reference's rank
+    (src/model_baseline.py:106-109) regrouped as (b, x//T, y//T, x%T, y%T, z), a bijection of the
+    rank, so every voxel's run holds the reference's points in the reference's order (see
+    reference_order()) and neighbours in the list are neighbours on the map."""
     grid: GridSpec
     B: int
     N: int
@@ -212,8 +214,8 @@ class Plan:
     fH: int
     fW: int
     cells: torch.Tensor          # (P) int32 output cell of each point, -1 if dropped
-    cell_start: torch.Tensor     # (n_cells + 1) int32: cell c owns sorted_points[cell_start[c]:cell_start[c+1]]
-    sorted_points: torch.Tensor  # (P) int32 point ids ordered by (cell, point id); first K entries valid
+    key_start: torch.Tensor      # (n_keys + 1) int32: key k owns sorted_points[key_start[k]:key_start[k+1]]
+    sorted_points: torch.Tensor  # (P) int32 point ids ordered by (key, point id); first K entries valid
     sorted_cells: torch.Tensor   # (P) int32 output cell of each sorted point, -1 beyond the K kept points
     counts: torch.Tensor         # (2) int32 {K, V}
 
@@ -223,6 +225,10 @@ class Plan:
 
     def shape(self, C: int) -> _abi.LssShape:
         return _abi.make_shape(self.B, self.N, self.D, self.fH, self.fW, C)
+
+    def keys_of_cells(self, cells: torch.Tensor) -> torch.Tensor:
+        """Tile-major sort key of output cells ((b*X + x)*Y + y)*Z + z (int64 tensor in, int64 out)."""
+        return keys_of_cells(cells, self.grid)
 
     def reference_order(self) -> torch.Tensor:
         """The kept points in the order of the reference's ``ranks.argsort()``
@@ -236,6 +242,26 @@ class Plan:
         ranks = torch.where(c >= 0, rest * self.B + b, torch.full_like(c, n_cells)).int()
         _, sp = sort_ranks(ranks.contiguous(), n_cells)
         return sp[:K]
+
+
+def key_tile() -> int:
+    return int(_abi.load().lss_plan_key_tile())
+
+
+def keys_of_cells(cells, grid: GridSpec):
+    """key = ((((b*XT + x//T)*YT + y//T)*T + x%T)*T + y%T)*Z + z for cell = ((b*X + x)*Y + y)*Z + z.
+    Works on torch tensors and numpy arrays (integer arithmetic only)."""
+    X, Y, Z = grid.nx
+    T = key_tile()
+    XT, YT = (X + T - 1) // T, (Y + T - 1) // T
+    z = cells % Z; t = cells // Z
+    y = t % Y; t = t // Y
+    x = t % X; b = t // X
+    return ((((b * XT + x // T) * YT + y // T) * T + x % T) * T + y % T) * Z + z
+
+
+def n_keys(grid: GridSpec, B: int) -> int:
+    return int(_abi.load().lss_plan_key_count(grid.c(), B))
 
 
 _WORKSPACES: Dict[Tuple, torch.Tensor] = {}
@@ -253,9 +279,9 @@ def _workspace(dev, stream: int, nbytes: int) -> torch.Tensor:
     return ws
 
 
-def _plan_outputs(P: int, n_cells: int, dev):
+def _plan_outputs(P: int, nkeys: int, dev):
     return (torch.empty(P, dtype=torch.int32, device=dev),
-            torch.empty(n_cells + 1, dtype=torch.int32, device=dev),
+            torch.empty(nkeys + 1, dtype=torch.int32, device=dev),
             torch.empty(P, dtype=torch.int32, device=dev),
             torch.empty(P, dtype=torch.int32, device=dev),
             torch.empty(2, dtype=torch.int32, device=dev))
@@ -271,17 +297,17 @@ def build_plan(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: Gr
     P = B * N * D * fH * fW
     st = _stream(dev)
     ws = _workspace(dev, st, _abi.load().lss_plan_workspace_bytes(shape, g))
-    cells, cell_start, sorted_points, sorted_cells, counts = _plan_outputs(P, grid.n_cells(B), dev)
+    cells, key_start, sorted_points, sorted_cells, counts = _plan_outputs(P, n_keys(grid, B), dev)
     try:
         _abi.call("lss_build_plan", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
                   _ptr(_f32c(rots)), _ptr(_f32c(trans)), _ptr(_f32c(intrins)),
                   _ptr(_f32c(post_rots)), _ptr(_f32c(post_trans)), g, shape, _ptr(cells),
-                  _ptr(cell_start), _ptr(sorted_points), _ptr(sorted_cells), _ptr(counts), _ptr(ws),
+                  _ptr(key_start), _ptr(sorted_points), _ptr(sorted_cells), _ptr(counts), _ptr(ws),
                   ws.numel(), st)
     except _abi.LssError:
         ws.zero_()  # a failed call may leave the control words dirty
         raise
-    return Plan(grid, B, N, D, fH, fW, cells, cell_start, sorted_points, sorted_cells, counts)
+    return Plan(grid, B, N, D, fH, fW, cells, key_start, sorted_points, sorted_cells, counts)
 
 
 def plan_from_geom(geom: torch.Tensor, grid: GridSpec) -> Plan:
@@ -294,14 +320,14 @@ def plan_from_geom(geom: torch.Tensor, grid: GridSpec) -> Plan:
     g = grid.c()
     st = _stream(dev)
     ws = _workspace(dev, st, _abi.load().lss_plan_from_geom_workspace_bytes(P, g, B))
-    cells, cell_start, sorted_points, sorted_cells, counts = _plan_outputs(P, grid.n_cells(B), dev)
+    cells, key_start, sorted_points, sorted_cells, counts = _plan_outputs(P, n_keys(grid, B), dev)
     try:
-        _abi.call("lss_build_plan_from_geom", _ptr(geom), g, B, P, _ptr(cells), _ptr(cell_start),
+        _abi.call("lss_build_plan_from_geom", _ptr(geom), g, B, P, _ptr(cells), _ptr(key_start),
                   _ptr(sorted_points), _ptr(sorted_cells), _ptr(counts), _ptr(ws), ws.numel(), st)
     except _abi.LssError:
         ws.zero_()
         raise
-    return Plan(grid, B, N, D, fH, fW, cells, cell_start, sorted_points, sorted_cells, counts)
+    return Plan(grid, B, N, D, fH, fW, cells, key_start, sorted_points, sorted_cells, counts)
 
 
 # --------------------------------------------------------------------------
@@ -357,7 +383,7 @@ class _LiftSplat(torch.autograd.Function):
         depth_t, feat_t = lift_stage(depth, feat, plan)
         bev = _alloc_bev(plan, C, dev)
         _abi.call("lss_liftsplat_fwd", _ptr(depth_t), _ptr(feat_t), _ptr(plan.sorted_points),
-                  _ptr(plan.sorted_cells), _ptr(plan.cell_start), plan.grid.c(), plan.shape(C),
+                  _ptr(plan.sorted_cells), _ptr(plan.key_start), plan.grid.c(), plan.shape(C),
                   _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
         ctx.plan = plan
         ctx.C = C
@@ -410,7 +436,7 @@ class _PoolDense(torch.autograd.Function):
             raise RuntimeError("x has %d points, plan has %d" % (x2.shape[0], plan.P))
         bev = _alloc_bev(plan, C, dev)
         _abi.call("lss_pool_dense_fwd", _ptr(x2), _ptr(plan.sorted_points), _ptr(plan.sorted_cells),
-                  _ptr(plan.cell_start), plan.grid.c(), plan.B, C, plan.P, _abi.LSS_BEV_NHWC, _ptr(bev),
+                  _ptr(plan.key_start), plan.grid.c(), plan.B, C, plan.P, _abi.LSS_BEV_NHWC, _ptr(bev),
                   _stream(dev))
         ctx.plan = plan
         ctx.x_shape = tuple(x.shape)

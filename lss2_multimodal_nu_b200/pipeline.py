@@ -75,7 +75,7 @@ class LiftSplatStep:
         # plan + staging buffers
         self.cells = torch.empty(self.P, **i32)
         self.sorted_points = torch.empty(self.P, **i32)
-        self.cell_start = torch.empty(grid.n_cells(B) + 1, **i32)
+        self.key_start = torch.empty(int(_abi.load().lss_plan_key_count(grid.c(), B)) + 1, **i32)
         self.sorted_cells = torch.empty(self.P, **i32)
         self.counts = torch.zeros(2, **i32)
         self.depth_t = torch.empty((BN * HW, D), **f32)
@@ -125,13 +125,13 @@ class LiftSplatStep:
         i = self.inputs
         _abi.call("lss_build_plan", p(self.us), p(self.vs), p(self.ds), p(i["rots"]), p(i["trans"]),
                   p(i["intrins"]), p(i["post_rots"]), p(i["post_trans"]), self._g, self._shape,
-                  p(self.cells), p(self.cell_start), p(self.sorted_points), p(self.sorted_cells),
+                  p(self.cells), p(self.key_start), p(self.sorted_points), p(self.sorted_cells),
                   p(self.counts), p(self._ws), self._ws.numel(), st)
 
     def enqueue_fwd(self, st: int) -> None:
         p = lambda t: t.data_ptr()
         _abi.call("lss_liftsplat_fwd", p(self.depth_t), p(self.feat_t), p(self.sorted_points),
-                  p(self.sorted_cells), p(self.cell_start), self._g, self._shape, _abi.LSS_BEV_NHWC,
+                  p(self.sorted_cells), p(self.key_start), self._g, self._shape, _abi.LSS_BEV_NHWC,
                   p(self._bev), st)
 
     def enqueue_bwd(self, st: int) -> None:

@@ -66,25 +66,24 @@ def axes_of(g):
 CAL = ("rots", "trans", "intrins", "post_rots", "post_trans")
 
 
-def cell_major(ref_sorted_points, P, B):
-    """The reference's sort order (by rank, batch digit least significant) regrouped stably by
-    sample: the order a stable sort by output cell gives (see functional.Plan)."""
-    ref = np.asarray(ref_sorted_points)
-    return ref[np.argsort(ref // (P // B), kind="stable")]
-
-
 def check_plan_tables(plan, ref_sorted_points):
-    """cell_start / sorted_points / cells are mutually consistent and carry the reference's order."""
-    K = len(ref_sorted_points)
-    cells = cpu(plan.cells); cs = cpu(plan.cell_start); sp = cpu(plan.sorted_points)[:K]
+    """key_start / sorted_points / sorted_cells / cells are mutually consistent and carry the
+    reference's order: the reference's argsort output (by rank), stably regrouped by the
+    tile-major key of each point's voxel."""
+    ref = np.asarray(ref_sorted_points)
+    K = len(ref)
+    cells = cpu(plan.cells).astype(np.int64); ks = cpu(plan.key_start); sp = cpu(plan.sorted_points)[:K]
+    nk = F.n_keys(plan.grid, plan.B)
     n_cells = plan.grid.n_cells(plan.B)
-    assert cs.shape == (n_cells + 1,) and cs[0] == 0 and cs[-1] == K and (np.diff(cs) >= 0).all()
-    assert (np.bincount(cells[cells >= 0], minlength=n_cells) == np.diff(cs)).all()
-    assert (sp == cell_major(ref_sorted_points, plan.P, plan.B)).all()
-    assert (cells[sp] == np.repeat(np.arange(n_cells), np.diff(cs))).all()
+    assert ks.shape == (nk + 1,) and ks[0] == 0 and ks[-1] == K and (np.diff(ks) >= 0).all()
+    keys = F.keys_of_cells(cells, plan.grid)                 # per point (garbage where cells < 0)
+    assert len(np.unique(F.keys_of_cells(np.arange(n_cells, dtype=np.int64), plan.grid))) == n_cells
+    assert (np.bincount(keys[cells >= 0], minlength=nk) == np.diff(ks)).all()
+    assert (sp == ref[np.argsort(keys[ref], kind="stable")]).all()
+    assert (keys[sp] == np.repeat(np.arange(nk), np.diff(ks))).all()
     sc = cpu(plan.sorted_cells)
     assert (sc[:K] == cells[sp]).all() and (sc[K:] == -1).all()
-    assert cpu(plan.counts).tolist() == [K, int((np.diff(cs) > 0).sum())]
+    assert cpu(plan.counts).tolist() == [K, int((np.diff(ks) > 0).sum())]
 
 
 FIXTURES = ["tiny", "edge_none_kept", "edge_one_voxel", "edge_randn_calib", "edge_nonfinite"]
@@ -182,7 +181,7 @@ def test_fused_plan_matches_stepwise(golden_dir, name):
     B = g["trans"].shape[0]
     plan = F.build_plan(us, vs, ds, *(dev(g[k]) for k in CAL), grid)
     step = F.plan_from_geom(dev(g["geom"]), grid)
-    for a in ("cells", "cell_start", "counts"):
+    for a in ("cells", "key_start", "counts"):
         assert (cpu(getattr(plan, a)) == cpu(getattr(step, a))).all(), a
     K = int(cpu(plan.counts)[0])
     assert K == len(g["ranks"])
@@ -197,12 +196,13 @@ def test_fused_plan_matches_stepwise(golden_dir, name):
     sk, _ = F.sort_ranks(q["ranks"], grid.n_cells(B))
     cell_range, counts, _, _ = F.intervals(sk, grid, B)
     cr = cpu(cell_range)
-    assert ((cr[:, 1] - cr[:, 0]) == np.diff(cpu(plan.cell_start))).all()
+    key_of = F.keys_of_cells(np.arange(grid.n_cells(B), dtype=np.int64), grid)
+    assert ((cr[:, 1] - cr[:, 0]) == np.diff(cpu(plan.key_start))[key_of]).all()
     assert cpu(counts).tolist() == cpu(plan.counts).tolist()
     # the workspace is reusable: a second call gives the same plan
     plan2 = F.build_plan(us, vs, ds, *(dev(g[k]) for k in CAL), grid)
     assert (cpu(plan2.sorted_points)[:K] == cpu(plan.sorted_points)[:K]).all()
-    assert (cpu(plan2.cell_start) == cpu(plan.cell_start)).all()
+    assert (cpu(plan2.key_start) == cpu(plan.key_start)).all()
 
 
 @pytest.mark.parametrize("name", FIXTURES)
