@@ -152,6 +152,7 @@ struct PoolFwdArgs {
 constexpr int kPoolThreads = 256;
 constexpr int kPoolWarps = kPoolThreads / 32;
 constexpr int kPoolChunk = 32;    // sorted points per reduce warp
+constexpr int kZeroBytes = 2048;  // zero block in shared memory: source of the bulk zero stores
 constexpr int kPoolRec = 64;      // staged records per warp: the chunk + the tail of its last interval
 
 template <int kVec> struct VecOf;
@@ -172,12 +173,21 @@ __device__ __forceinline__ void vec_fma(float d, const float4& f, float4& a) {
   a.x = fmaf(d, f.x, a.x); a.y = fmaf(d, f.y, a.y); a.z = fmaf(d, f.z, a.z); a.w = fmaf(d, f.w, a.w);
 }
 
+#ifndef LSS_FWD_MINB
+#define LSS_FWD_MINB 4
+#endif
+#ifndef LSS_FWD_STAGES
+#define LSS_FWD_STAGES 4
+#endif
+#ifndef LSS_BWD_MINB
+#define LSS_BWD_MINB 4
+#endif
 template <bool kFused, int kVec>
-__global__ void __launch_bounds__(kPoolThreads)
+__global__ void __launch_bounds__(kPoolThreads, LSS_FWD_MINB)
 pool_fwd_nhwc_kernel(PoolFwdArgs a) {
   using V = typename VecOf<kVec>::type;
   constexpr int kU = 4;                                      // gathers per pipeline stage
-  constexpr int kS = kVec == 4 ? 2 : 4;                      // stages: (kS - 1) * kU gathers in flight
+  constexpr int kS = kVec == 4 ? 2 : LSS_FWD_STAGES;         // stages: (kS - 1) * kU gathers in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) phase_stamp_any(2, warp * 2);
 
@@ -186,10 +196,17 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
   // coalesced load; every group of 8 keys is 8 consecutive voxels of one tile row, i.e. one
   // contiguous piece of the map, covered with 128-bit stores wherever the voxel is empty.
   if (static_cast<int>(blockIdx.x) < a.fill_ctas) {
+    // the zeros come from a 2 KB block of shared memory and leave through the TMA engine (bulk
+    // async stores, one instruction per contiguous piece), so they occupy neither the warps' issue
+    // slots nor the load/store queues the REDUCE warps' gathers go through
+    __shared__ __align__(128) float4 s_zero[kZeroBytes / 16];
+    for (int e = threadIdx.x; e < kZeroBytes / 16; e += kPoolThreads) s_zero[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const uint32_t zsrc = static_cast<uint32_t>(__cvta_generic_to_shared(s_zero));
     const int n_blocks = (a.keys.n_keys + 31) >> 5;
     const int stride = a.fill_ctas * kPoolWarps;
-    const int G4 = a.C >> 2;                                 // float4 per line
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t line_bytes = static_cast<uint32_t>(a.C) * 4u;
     int blk = blockIdx.x * kPoolWarps + warp;
     if (blk >= n_blocks) return;
     auto bounds = [&](int bk, int& lo, int& hi) {
@@ -205,28 +222,31 @@ pool_fwd_nhwc_kernel(PoolFwdArgs a) {
       if (nxt < n_blocks) bounds(nxt, nlo, nhi);             // prefetch before the stores go out
       const int k = (blk << 5) + lane;
       const int mycell = (k < a.keys.n_keys) ? a.keys.cell_of_key(static_cast<uint32_t>(k)) : -1;
-      const uint32_t empty = __ballot_sync(0xffffffffu, mycell >= 0 && hi == lo);
+      const bool empty = mycell >= 0 && hi == lo;
+      const uint32_t em = __ballot_sync(0xffffffffu, empty);
+      // maximal runs of empty keys inside a group of 8 (= contiguous voxels): the first lane of a
+      // run stores the whole run, at most kZeroBytes at a time
       if (empty) {
-        const int n4 = 8 * G4;                               // float4 per group of 8 voxels
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t em = (empty >> (8 * g)) & 0xffu;
-          const int base = __shfl_sync(0xffffffffu, mycell, 8 * g);
-          if (em == 0u) continue;
-          float4* dst = reinterpret_cast<float4*>(a.bev + (size_t)base * a.C);
-          if (em == 0xffu) {
-            for (int e = lane; e < n4; e += 32) dst[e] = z4;
-          } else {
-            for (int e = lane; e < n4; e += 32) {
-              const uint32_t line = a.div_g4.div(static_cast<uint32_t>(e));
-              if ((em >> line) & 1u) dst[e] = z4;
-            }
+        const uint32_t g8 = (em >> (lane & 24)) & 0xffu;      // this group's 8 bits
+        const int j = lane & 7;
+        if (j == 0 || !((g8 >> (j - 1)) & 1u)) {              // run head
+          const uint32_t rest = (~(g8 >> j)) & 0xffu;         // first non-empty key after the head
+          const int len = rest ? __ffs(rest) - 1 : 8 - j;
+          char* dst = reinterpret_cast<char*>(a.bev) + (size_t)mycell * line_bytes;
+          uint32_t left = static_cast<uint32_t>(len) * line_bytes;
+          while (left) {
+            const uint32_t n = left < static_cast<uint32_t>(kZeroBytes) ? left : static_cast<uint32_t>(kZeroBytes);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"(zsrc), "r"(n) : "memory");
+            dst += n; left -= n;
           }
         }
       }
       if (nxt >= n_blocks) break;
       blk = nxt; lo = nlo; hi = nhi;
     }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the zero block must outlive the reads
     if (lane == 0) phase_stamp_any(2, warp * 2 + 1);
     return;
   }
@@ -415,7 +435,7 @@ constexpr int kBwdWarps = kBwdThreads / 32;
 constexpr int kBwdChunk = 128;   // depth bins staged per warp at a time
 
 template <int kLanes>
-__global__ void __launch_bounds__(kBwdThreads, 3)
+__global__ void __launch_bounds__(kBwdThreads, LSS_BWD_MINB)
 liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
   constexpr int kPts = 32 / kLanes;                 // points per warp step
   constexpr int kUnroll = kLanes >= 8 ? 8 : kLanes; // steps in flight

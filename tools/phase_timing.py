@@ -39,10 +39,10 @@ for _ in range(5):
 torch.cuda.synchronize()
 lib = _abi.load()
 lib.lss_debug_phase_ts.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
-n_cells = grid.n_cells(cfg.B)
-fill = min(((n_cells + 31) // 32 + 7) // 8, 148)
+n_keys = F.n_keys(grid, cfg.B)
+fill = min(((n_keys + 31) // 32 + 7) // 8, 148)
 fill = int(os.environ.get("LSS_FILL_CTAS", fill))
-rows = min(40, 8704 // (cfg.C * 4)); chunk = min(32, rows - min(8, rows // 4)); nblk = min(4096, fill + (cfg.P + chunk * 8 - 1) // (chunk * 8))
+chunk = 32; nblk = min(4096, fill + (cfg.P + chunk * 8 - 1) // (chunk * 8))
 buf = np.zeros(4096 * 16, np.uint64)
 lib.lss_debug_phase_ts(2, buf.ctypes.data, buf.size)
 ts = buf.reshape(4096, 8, 2)[:nblk].astype(np.int64)
