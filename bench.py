@@ -175,6 +175,25 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def bind_to_gpu_cpus(index):
+    """Pin this process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe root), so that
+    pinned host buffers are allocated next to it.  Returns the previous affinity set (None if unchanged)."""
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(index)
+        before = os.sched_getaffinity(0)
+        words = N.nvmlDeviceGetCpuAffinity(h, (max(before) // 64) + 1)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= before
+        if cpus and cpus != before:
+            os.sched_setaffinity(0, cpus)
+            return before
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
@@ -189,6 +208,7 @@ def run_ours(args, cfg):
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = bind_to_gpu_cpus(local)        # pinned buffers and the submitting thread next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _abi.load()
@@ -251,6 +271,25 @@ def run_ours(args, cfg):
     clocks.start()
     elapsed_ms = timed(args.steps)
     clocks.stop()
+    barrier()
+    # the same steps strictly one after the other (one batch in flight), for reference
+    serial_lane = lanes[0]
+    def timed_serial(n):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        serial_lane.wait_stream(stream)
+        e0.record(serial_lane)
+        for i in range(n):
+            d = steps[i % len(steps)]
+            with torch.cuda.stream(serial_lane):
+                if d._graph is not None:
+                    d._graph.replay()
+                else:
+                    d._enqueue(serial_lane, d._side)
+        e1.record(serial_lane)
+        serial_lane.synchronize()
+        return e0.elapsed_time(e1)
+    timed_serial(8)
+    serial_ms = timed_serial(min(args.steps, 200)) / min(args.steps, 200)
     barrier()
     value = shard.aggregate_throughput(cfg.B * args.steps, elapsed_ms, dev)   # all samples / slowest rank
     elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
@@ -338,13 +377,16 @@ def run_ours(args, cfg):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e2e_run(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    reps = []
+    for _ in range(3):                        # host wall clock is noisy: median of three runs of e2e_steps
+        t0 = time.perf_counter()
+        e2e_run(e2e_steps)
+        torch.cuda.synchronize()
+        reps.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = sorted(reps)[1]
     if os.environ.get("LSS_E2E_DEBUG"):
         sys.stderr.write("e2e host: submit %.1f us, collect %.1f us per step\n" % (
-            dbg["sub"] / (e2e_steps + 40) * 1e6, dbg["col"] / (e2e_steps + 40) * 1e6))
+            dbg["sub"] / (3 * e2e_steps + 40) * 1e6, dbg["col"] / (3 * e2e_steps + 40) * 1e6))
     e2e_value = shard.aggregate_throughput(cfg.B * e2e_steps, e2e_ms, dev)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
            "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
@@ -352,7 +394,7 @@ def run_ours(args, cfg):
                    "d_depth+d_feat out (one packed D2H), both copies inside the slot's CUDA graph, every step's "
                    "result read on the host, six steps in flight (copies overlap kernels); upstream dBEV "
                    "stays on the device; host wall clock",
-           "host_link_gbs": link}
+           "host_link_gbs": link, "repeats_ms_per_step": [round(r / e2e_steps, 4) for r in reps]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -366,9 +408,13 @@ def run_ours(args, cfg):
                          % (args.sets, 2 * alg["bev"] / 1e6),
                    "launch": "stream launches" if args.no_graph else "cuda-graph replay (lift staging || plan)",
                    "step": "camera prep+geometry+sort+intervals, lift staging, fused fwd, fused bwd"},
+        "serial": {"ms_per_step": serial_ms, "value": cfg.B * world / (serial_ms * 1e-3), "unit": UNIT,
+                   "note": "one batch in flight: every kernel of a step waits for the previous step"},
         "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
         "gpu_launches": KERNELS_PER_STEP * args.steps,
     }
+    if all_cpus:
+        os.sched_setaffinity(0, all_cpus)     # the CPU baseline below uses every host core
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_port_run(cfg, steps=60, warmup=1, budget_s=12.0)
         line["cpu_baseline"] = {"value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",

@@ -2,6 +2,7 @@
 
     python -m lss2_multimodal_nu_b200.run train.py --dataroot ... --bsize 8
     python -m lss2_multimodal_nu_b200.run predict.py ...
+    LSS_STATIC_CALIB=1 python -m lss2_multimodal_nu_b200.run predict.py ...   # fixed rig: build the plan once
 
 The script's directory is put on sys.path (so ``from src... import`` resolves as
 it does when the script is run directly), the reference classes are patched
@@ -22,6 +23,8 @@ def main(argv=None):
     sys.path.insert(0, os.path.dirname(script))
     from . import patch
     n = patch.install_reference_classes()
+    if os.environ.get("LSS_STATIC_CALIB"):
+        patch.STATIC_BY_DEFAULT = True
     if n == 0:
         print("lss2_multimodal_nu_b200.run: no reference model classes found next to %s" % script,
               file=sys.stderr)

@@ -438,3 +438,104 @@ def test_step_object_and_host_pipeline_match_functional_api(golden_dir):
     assert len(outs) == 5
     for o in outs:
         assert torch.equal(o["d_depth"], depth.grad.cpu()) and torch.equal(o["d_feat"], feat.grad.cpu())
+
+
+# ---------------------------------------------------------------------------
+# the drop-in boundary: the reference's module methods, rebound by patch.install
+# ---------------------------------------------------------------------------
+class _CamEncodeStandIn(torch.nn.Module):
+    """Attribute surface of the reference's CamEncode that the patched methods touch
+    (src/modules.py:69-91): D, C, a depthnet conv producing D + C channels, get_depth_dist."""
+
+    def __init__(self, D, C, cin):
+        super().__init__()
+        self.D, self.C = D, C
+        self.depthnet = torch.nn.Conv2d(cin, D + C, kernel_size=1, padding=0)
+
+    def get_depth_dist(self, x, eps=1e-20):
+        return x.softmax(dim=1)
+
+
+class _LssStandIn(torch.nn.Module):
+    """Attribute surface of the reference's LSS class (src/model_baseline.py:11-48)."""
+
+    def __init__(self, cfg, cin=16):
+        super().__init__()
+        dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+        self.dx = torch.nn.Parameter(torch.from_numpy(dx), requires_grad=False)
+        self.bx = torch.nn.Parameter(torch.from_numpy(bx), requires_grad=False)
+        self.nx = torch.nn.Parameter(torch.from_numpy(nx), requires_grad=False)
+        fr = O.create_frustum(cfg.final_dim, cfg.downsample, cfg.dbound)
+        self.frustum = torch.nn.Parameter(torch.from_numpy(fr), requires_grad=False)
+        self.D, self.camC, self.bsize, self.downsample = fr.shape[0], cfg.C, cfg.B, cfg.downsample
+        self.camencode = _CamEncodeStandIn(self.D, cfg.C, cin)
+
+    # the four methods the reference defines on the class (bodies: the PyTorch implementation the
+    # patch replaces; never reached here)
+    def get_geometry(self, rots, trans, intrins, post_rots, post_trans): raise NotImplementedError
+    def get_cam_feats(self, x): raise NotImplementedError
+    def voxel_pooling(self, geom_feats, x): raise NotImplementedError
+    def get_voxels(self, x, rots, trans, intrins, post_rots, post_trans): raise NotImplementedError
+
+
+def test_patched_module_api_end_to_end():
+    """get_geometry / get_cam_feats / voxel_pooling / get_voxels on a module with the reference's
+    attribute surface: shapes, values and gradients against the oracle, the two call paths agree,
+    no parameter or buffer is added, and the opt-in static-calibration plan is built once."""
+    from lss2_multimodal_nu_b200 import patch
+    cfg = S.config("tiny")
+    torch.manual_seed(3)
+    m = _LssStandIn(cfg).to(DEV)
+    keys = list(m.state_dict().keys())
+    patch.install(m)
+    assert list(m.state_dict().keys()) == keys
+    cal = S.make_calibration(cfg, 11)
+    calib = [dev(cal[k]) for k in CAL]
+    BN = cfg.B * cfg.N
+    x = torch.randn(BN, 16, cfg.fH, cfg.fW, device=DEV, requires_grad=True)
+
+    # path 1: the fused entry (reference src/model_baseline.py:128-133)
+    bev = m.get_voxels(x, *calib)
+    X, Y, Z = (int(v) for v in m.nx)
+    assert tuple(bev.shape) == (cfg.B, cfg.C * Z, X, Y)
+    # oracle on the module's own depth / feat
+    with torch.no_grad():
+        y = m.camencode.depthnet(x)
+        depth = y[:, :m.D].softmax(1); feat = y[:, m.D:m.D + cfg.C]
+    geom = O.get_geometry(cpu(m.frustum), **cal)
+    dx, bx, nx = cpu(m.dx), cpu(m.bx), cpu(m.nx)
+    want, _ = O.voxel_pooling(geom, O.lift(cpu(depth).astype(np.float64), cpu(feat).astype(np.float64)),
+                              dx, bx, nx, cfg.B, mode="exact")
+    close(cpu(bev), want)
+    gout = torch.randn_like(bev)
+    bev.backward(gout)
+    gx1 = x.grad.clone(); gw1 = m.camencode.depthnet.weight.grad.clone()
+    assert torch.isfinite(gx1).all() and gx1.abs().sum() > 0
+
+    # path 2: the three separate methods (src/model_baseline.py:50, :72, :84), same answers
+    x.grad = None; m.camencode.depthnet.weight.grad = None
+    g = m.get_geometry(*calib)
+    assert tuple(g.shape) == (cfg.B, cfg.N, m.D, cfg.fH, cfg.fW, 3)
+    nan = np.isnan(geom)
+    assert (cpu(g).view(np.uint32)[~nan] == geom.view(np.uint32)[~nan]).all()
+    lifted = m.get_cam_feats(x)
+    assert tuple(lifted.shape) == (cfg.B, cfg.N, m.D, cfg.fH, cfg.fW, cfg.C)
+    bev2 = m.voxel_pooling(g, lifted)
+    assert torch.equal(bev2, bev.detach())
+    bev2.backward(gout)
+    assert torch.equal(x.grad, gx1)
+    # (the conv's own weight-gradient kernel is not bit-reproducible run to run)
+    assert torch.allclose(m.camencode.depthnet.weight.grad, gw1, rtol=1e-4, atol=1e-5)
+    # a dense tensor in place of the lazy handle (the literal signature) gives the same map
+    bev3 = m.voxel_pooling(g.clone(), lifted.materialize())
+    close(cpu(bev3), want)
+
+    # evaluation with a fixed rig: the plan is built once
+    c = patch._cache(m)
+    patch.static_calibration(m, True)
+    n0 = c.plan_builds
+    with torch.no_grad():
+        a = m.get_voxels(x, *calib); b = m.get_voxels(x, *calib); d = m.voxel_pooling(m.get_geometry(*calib), m.get_cam_feats(x))
+    assert c.plan_builds == n0 + 1
+    assert torch.equal(a, bev.detach()) and torch.equal(b, a) and torch.equal(d, a)
+    patch.static_calibration(m, False)
