@@ -213,6 +213,13 @@ int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGri
  * ------------------------------------------------------------------------- */
 int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* shape,
                    float* d_depth_t, float* d_feat_t, void* stream);
+/* The same with a batch stride (in elements) per input, so depth and feat may be channel slices of
+ * ONE conv output (B*N, D+C, fH, fW) as CamEncode produces it (src/modules.py:74,82-84), and with
+ * softmax != 0 the first input holds the depth LOGITS: the depth distribution
+ * x[:, :D].softmax(dim=1) (src/modules.py:76-77) is computed while staging (D <= 128). */
+int lss_lift_stage_ex(const float* d_depth_or_logits, int64_t depth_batch_stride, const float* d_feat,
+                      int64_t feat_batch_stride, const LssShape* shape, int32_t softmax,
+                      float* d_depth_t, float* d_feat_t, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K4  fused lift + splat forward.  bev[cell, c] = sum over the cell's points of
@@ -229,6 +236,14 @@ int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32
 int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
                       const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
                       int32_t layout, float* d_ddepth, float* d_dfeat, void* stream);
+/* The same with output batch strides (the two gradients may be channel slices of one tensor) and,
+ * with softmax != 0, the softmax backward fused: the first output receives the gradient of the depth
+ * LOGITS, p * (d_depth - sum_d p * d_depth), p = d_depth_t (autograd of src/modules.py:77; D <= 128). */
+int lss_liftsplat_bwd_ex(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
+                         const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
+                         int32_t layout, int32_t softmax, float* d_ddepth_or_dlogits,
+                         int64_t ddepth_batch_stride, float* d_dfeat, int64_t dfeat_batch_stride,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -323,19 +323,43 @@ int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGri
   return LSS_OK;
 }
 
-int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* shape,
-                   float* d_depth_t, float* d_feat_t, void* stream) {
+static int lift_stage_common(const float* d_depth, long long depth_bs, const float* d_feat, long long feat_bs,
+                             const LssShape* shape, int softmax, float* d_depth_t, float* d_feat_t,
+                             cudaStream_t st) {
   LSS_REQUIRE(d_depth && d_feat && d_depth_t && d_feat_t, LSS_ERR_NULL_POINTER);
   int rc = check_shape(shape);
   if (rc) return rc;
   const int HW = shape->fH * shape->fW, BN = shape->B * shape->N;
   const int R = shape->D > shape->C ? shape->D : shape->C;
   LSS_REQUIRE(BN * 2 <= 65535, LSS_ERR_BAD_DIMENSION);
+  LSS_REQUIRE(depth_bs >= (long long)shape->D * HW && feat_bs >= (long long)shape->C * HW, LSS_ERR_BAD_DIMENSION);
   dim3 grid((HW + 31) / 32, (R + 31) / 32, BN * 2);
-  lift_stage_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_depth, d_feat, shape->D, shape->C, HW,
-                                                        d_depth_t, d_feat_t);
+  if (softmax) {
+    LSS_REQUIRE(shape->D <= kSoftmaxMaxD, LSS_ERR_UNSUPPORTED);
+    lift_stage_softmax_kernel<<<dim3((HW + 31) / 32, BN), 256, 0, st>>>(d_depth, depth_bs, shape->D, HW, d_depth_t);
+    LSS_LAUNCH_CHECK("lift_stage_softmax_kernel");
+    lift_stage_kernel<<<grid, 256, 0, st>>>(nullptr, 0, d_feat, feat_bs, shape->D, shape->C, HW, d_depth_t, d_feat_t);
+  } else {
+    lift_stage_kernel<<<grid, 256, 0, st>>>(d_depth, depth_bs, d_feat, feat_bs, shape->D, shape->C, HW, d_depth_t,
+                                            d_feat_t);
+  }
   LSS_LAUNCH_CHECK("lift_stage_kernel");
   return LSS_OK;
+}
+
+int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* shape,
+                   float* d_depth_t, float* d_feat_t, void* stream) {
+  if (check_shape(shape) != LSS_OK) return check_shape(shape);
+  const long long HW = (long long)shape->fH * shape->fW;
+  return lift_stage_common(d_depth, shape->D * HW, d_feat, shape->C * HW, shape, 0, d_depth_t, d_feat_t,
+                           as_stream(stream));
+}
+
+int lss_lift_stage_ex(const float* d_depth_or_logits, int64_t depth_batch_stride, const float* d_feat,
+                      int64_t feat_batch_stride, const LssShape* shape, int32_t softmax,
+                      float* d_depth_t, float* d_feat_t, void* stream) {
+  return lift_stage_common(d_depth_or_logits, depth_batch_stride, d_feat, feat_batch_stride, shape, softmax ? 1 : 0,
+                           d_depth_t, d_feat_t, as_stream(stream));
 }
 
 int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32_t* d_sorted_points,
@@ -351,9 +375,10 @@ int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32
                          layout, d_bev, as_stream(stream));
 }
 
-int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
-                      const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                      int32_t layout, float* d_ddepth, float* d_dfeat, void* stream) {
+static int liftsplat_bwd_common(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
+                                const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
+                                int32_t layout, int softmax, float* d_ddepth, long long ddepth_bs,
+                                float* d_dfeat, long long dfeat_bs, cudaStream_t st) {
   LSS_REQUIRE(d_dbev && d_depth_t && d_feat_t && d_cells && d_ddepth && d_dfeat, LSS_ERR_NULL_POINTER);
   int rc = check_shape(shape);
   if (rc) return rc;
@@ -362,22 +387,43 @@ int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* 
   if (rc) return rc;
   LSS_REQUIRE(shape->C % 4 == 0 && aligned16(d_dbev) && aligned16(d_feat_t), LSS_ERR_MISALIGNED);
   LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
+  const long long HW = (long long)shape->fH * shape->fW;
+  LSS_REQUIRE(ddepth_bs >= shape->D * HW && dfeat_bs >= shape->C * HW, LSS_ERR_BAD_DIMENSION);
+  LSS_REQUIRE(!softmax || shape->D <= kBwdChunk, LSS_ERR_UNSUPPORTED);
   PoolBwdArgs a;
   a.dbev = reinterpret_cast<const float4*>(d_dbev); a.depth_t = d_depth_t;
   a.feat_t = reinterpret_cast<const float4*>(d_feat_t); a.cells = d_cells;
-  a.ddepth = d_ddepth; a.dfeat = d_dfeat;
+  a.ddepth = d_ddepth; a.dfeat = d_dfeat; a.ddepth_bs = ddepth_bs; a.dfeat_bs = dfeat_bs; a.softmax = softmax;
   a.D = shape->D; a.fH = shape->fH; a.fW = shape->fW; a.C = shape->C; a.G = shape->C / 4;
   a.n_pix = shape->B * shape->N * shape->fH * shape->fW;
   a.div_fh = FastDiv((uint32_t)shape->fH); a.div_fw = FastDiv((uint32_t)shape->fW);
   LSS_REQUIRE((long long)g.n_cells * a.G < (1ll << 31), LSS_ERR_BAD_DIMENSION);
   const int G = a.G;
   const int blocks = (a.n_pix + kBwdWarps - 1) / kBwdWarps;
-  cudaStream_t st = as_stream(stream);
   if (G <= 4) return launch_bwd<4>(a, blocks, st);
   if (G <= 8) return launch_bwd<8>(a, blocks, st);
   if (G <= 16) return launch_bwd<16>(a, blocks, st);
   if (G <= 32) return launch_bwd<32>(a, blocks, st);
   return LSS_ERR_UNSUPPORTED;
+}
+
+int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
+                      const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
+                      int32_t layout, float* d_ddepth, float* d_dfeat, void* stream) {
+  if (check_shape(shape) != LSS_OK) return check_shape(shape);
+  const long long HW = (long long)shape->fH * shape->fW;
+  return liftsplat_bwd_common(d_dbev, d_depth_t, d_feat_t, d_cells, grid, shape, layout, 0, d_ddepth,
+                              shape->D * HW, d_dfeat, shape->C * HW, as_stream(stream));
+}
+
+int lss_liftsplat_bwd_ex(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
+                         const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
+                         int32_t layout, int32_t softmax, float* d_ddepth_or_dlogits,
+                         int64_t ddepth_batch_stride, float* d_dfeat, int64_t dfeat_batch_stride,
+                         void* stream) {
+  return liftsplat_bwd_common(d_dbev, d_depth_t, d_feat_t, d_cells, grid, shape, layout, softmax ? 1 : 0,
+                              d_ddepth_or_dlogits, ddepth_batch_stride, d_dfeat, dfeat_batch_stride,
+                              as_stream(stream));
 }
 
 size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid) {

@@ -82,13 +82,15 @@ intervals_kernel(IntervalArgs a) {
 // grid = (ceil(HW/32), ceil(max(D,C)/32), BN * 2)  [z even: depth, odd: feat]
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-lift_stage_kernel(const float* __restrict__ depth, const float* __restrict__ feat, int D, int C,
-                  int HW, float* __restrict__ depth_t, float* __restrict__ feat_t) {
+lift_stage_kernel(const float* __restrict__ depth, long long depth_bs, const float* __restrict__ feat,
+                  long long feat_bs, int D, int C, int HW, float* __restrict__ depth_t,
+                  float* __restrict__ feat_t) {
   __shared__ float tile[32][33];
   const int which = blockIdx.z & 1;
   const int bn = blockIdx.z >> 1;
   const int R = which ? C : D;
-  const float* src = (which ? feat : depth) + (size_t)bn * R * HW;
+  if (!which && depth == nullptr) return;              // depth staged elsewhere (softmax variant)
+  const float* src = which ? feat + (size_t)bn * feat_bs : depth + (size_t)bn * depth_bs;
   float* dst = (which ? feat_t : depth_t) + (size_t)bn * HW * R;
   const int r0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   if (r0 >= R) return;
@@ -103,6 +105,47 @@ lift_stage_kernel(const float* __restrict__ depth, const float* __restrict__ fea
   for (int k = 0; k < 4; ++k) {
     const int p = p0 + ty + k * 8, r = r0 + tx;
     if (p < HW && r < R) dst[(size_t)p * R + r] = tile[tx][ty + k * 8];
+  }
+}
+
+// Producer fusion: the depth distribution is softmax over the D logit channels
+// (reference src/modules.py:76-77, `x.softmax(dim=1)`), computed here while staging, so the
+// probabilities are written once, pixel-major, and the (B*N, D, fH, fW) probability tensor of the
+// reference never exists.  One CTA = 32 pixels x all D logits (tile in shared memory):
+// p = exp(x - max) / sum, the expression torch evaluates.
+constexpr int kSoftmaxMaxD = 128;
+__global__ void __launch_bounds__(256)
+lift_stage_softmax_kernel(const float* __restrict__ logits, long long logits_bs, int D, int HW,
+                          float* __restrict__ depth_t) {
+  __shared__ float tile[kSoftmaxMaxD][33];
+  __shared__ float s_max[32], s_inv[32];
+  const int bn = blockIdx.y, p0 = blockIdx.x * 32;
+  const float* src = logits + (size_t)bn * logits_bs;
+  float* dst = depth_t + (size_t)bn * HW * D;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < D; r += 8) {
+    const int p = p0 + tx;
+    tile[r][tx] = (p < HW) ? src[(size_t)r * HW + p] : 0.0f;
+  }
+  __syncthreads();
+  if (ty == 0) {                                      // one lane per pixel: max, then the sum of exp
+    float m = tile[0][tx];
+    for (int r = 1; r < D; ++r) m = fmaxf(m, tile[r][tx]);
+    float sum = 0.f;
+    for (int r = 0; r < D; ++r) {
+      const float e = expf(tile[r][tx] - m);
+      tile[r][tx] = e;
+      sum += e;
+    }
+    s_max[tx] = m;
+    s_inv[tx] = sum;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {                  // pixel k of the tile, lanes along d: coalesced rows
+    const int p = p0 + k;
+    if (p >= HW) continue;
+    const float sum = s_inv[k];
+    for (int r = tx; r < D; r += 32) dst[(size_t)p * D + r] = tile[r][k] / sum;
   }
 }
 
@@ -423,8 +466,10 @@ struct PoolBwdArgs {
   const float* depth_t;     // (BN*HW, D)
   const float4* feat_t;     // (BN*HW, G)
   const int32_t* cells;     // (BN, D, fH, fW)
-  float* ddepth;            // (BN, D, fH, fW)
-  float* dfeat;             // (BN, C, fH, fW)
+  float* ddepth;            // (BN, D, fH, fW) with batch stride ddepth_bs: d_depth, or d_logits when softmax
+  float* dfeat;             // (BN, C, fH, fW) with batch stride dfeat_bs
+  long long ddepth_bs, dfeat_bs;
+  int softmax;              // 1: depth_t = softmax(logits); emit d_logits = p * (d_depth - sum_d p * d_depth)
   int D, fH, fW, C, G;
   int n_pix;                // BN * fH * fW
   FastDiv div_fh, div_fw;
@@ -444,6 +489,7 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
   constexpr int kLogU = kUnroll == 8 ? 3 : 2;
   static_assert(kBwdChunk % kRound == 0, "chunk must hold whole rounds");
   __shared__ int2 s_cd[kBwdWarps][kBwdChunk];       // {output cell, depth bits} of the staged bins
+  __shared__ float s_dd[kBwdWarps][kBwdChunk];      // d_depth of the pixel (softmax backward needs all of them)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // pixel of this warp: h fastest, so a CTA is one image column (bn, w) when fH == 8
@@ -526,8 +572,23 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
         }
       }
       const int d = dc + d0 + my_u * kPts + grp;
-      if (writer && d < a.D) a.ddepth[((size_t)bn * a.D + d) * HW + col] = static_cast<float>(dot[0]);
+      if (writer && d < a.D) {
+        if (a.softmax) s_dd[warp][d] = static_cast<float>(dot[0]);        // D <= kBwdChunk (host)
+        else a.ddepth[(size_t)bn * a.ddepth_bs + (size_t)d * HW + col] = static_cast<float>(dot[0]);
+      }
     }
+  }
+  if (a.softmax) {
+    // softmax backward (reference: autograd of x.softmax(dim=1), src/modules.py:77), fused:
+    // d_logit[d] = p[d] * (d_depth[d] - sum_d' p[d'] * d_depth[d'])
+    __syncwarp();
+    double sp = 0.0;
+    for (int l = lane; l < a.D; l += 32) sp += static_cast<double>(__int_as_float(cd[l].y)) * static_cast<double>(s_dd[warp][l]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    const float spf = static_cast<float>(sp);
+    for (int l = lane; l < a.D; l += 32)
+      a.ddepth[(size_t)bn * a.ddepth_bs + (size_t)l * HW + col] = __int_as_float(cd[l].y) * (s_dd[warp][l] - spf);
   }
   // fold the kPts point-groups of the warp together
 #pragma unroll
@@ -538,7 +599,7 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
     acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
   }
   if (grp == 0 && lane_active) {
-    float* df = a.dfeat + ((size_t)bn * a.C + sub * 4) * HW + col;
+    float* df = a.dfeat + (size_t)bn * a.dfeat_bs + (size_t)(sub * 4) * HW + col;
     df[0] = acc.x; df[HW] = acc.y; df[2 * (size_t)HW] = acc.z; df[3 * (size_t)HW] = acc.w;
   }
 }

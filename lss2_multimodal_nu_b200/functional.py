@@ -421,6 +421,70 @@ def lift_splat(depth: torch.Tensor, feat: torch.Tensor, plan: Plan,
     return out
 
 
+def _batch_strided(t: torch.Tensor) -> bool:
+    """True when every batch item of a (BN, R, H, W) tensor is dense (only the batch stride is free),
+    i.e. the tensor is a channel slice of a contiguous conv output."""
+    BN, R, H, W = t.shape
+    return t.dtype == torch.float32 and t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W \
+        and t.stride(0) >= R * H * W
+
+
+class _LiftSplatLogits(torch.autograd.Function):
+    """lift + splat straight from the CamEncode conv output y = depthnet(x) (reference
+    src/modules.py:82-84): channels [0, D) are the depth LOGITS, [D, D+C) the context features.
+    The softmax of src/modules.py:77, the channel split and the staging transposes are one pass
+    (lss_lift_stage_ex), the softmax backward is fused into K5 (lss_liftsplat_bwd_ex), and the
+    gradient comes back as ONE tensor shaped like y."""
+
+    @staticmethod
+    def forward(ctx, y, D: int, C: int, plan: Plan):
+        dev = _need_cuda(y)
+        if C % 4 != 0:
+            raise RuntimeError("C must be a multiple of 4 (128-bit channel vectors), got %d" % C)
+        BN, R, fH, fW = y.shape
+        if R < D + C or (BN, D, fH, fW) != (plan.B * plan.N, plan.D, plan.fH, plan.fW):
+            raise RuntimeError("conv output %s does not match D=%d C=%d and the plan (B=%d N=%d D=%d fH=%d fW=%d)"
+                               % (tuple(y.shape), D, C, plan.B, plan.N, plan.D, plan.fH, plan.fW))
+        ctx.in_dtype = y.dtype
+        y32 = y if _batch_strided(y) else _f32c(y)
+        HW = fH * fW
+        depth_t = torch.empty((BN * HW, D), dtype=torch.float32, device=dev)
+        feat_t = torch.empty((BN * HW, C), dtype=torch.float32, device=dev)
+        esz = 4
+        _abi.call("lss_lift_stage_ex", y32.data_ptr(), y32.stride(0), y32.data_ptr() + D * HW * esz,
+                  y32.stride(0), plan.shape(C), 1, _ptr(depth_t), _ptr(feat_t), _stream(dev))
+        bev = _alloc_bev(plan, C, dev)
+        _abi.call("lss_liftsplat_fwd", _ptr(depth_t), _ptr(feat_t), _ptr(plan.sorted_points),
+                  _ptr(plan.sorted_cells), _ptr(plan.key_start), plan.grid.c(), plan.shape(C),
+                  _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
+        ctx.plan, ctx.D, ctx.C, ctx.R = plan, D, C, R
+        ctx.save_for_backward(depth_t, feat_t)
+        return bev.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        depth_t, feat_t = ctx.saved_tensors
+        plan, D, C, R = ctx.plan, ctx.D, ctx.C, ctx.R
+        dev = grad_bev.device
+        g = _as_nhwc(grad_bev)
+        BN, HW = plan.B * plan.N, plan.fH * plan.fW
+        dy = (torch.zeros if R > D + C else torch.empty)((BN, R, plan.fH, plan.fW), dtype=torch.float32, device=dev)
+        _abi.call("lss_liftsplat_bwd_ex", _ptr(g), _ptr(depth_t), _ptr(feat_t), _ptr(plan.cells),
+                  plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC, 1, dy.data_ptr(), R * HW,
+                  dy.data_ptr() + D * HW * 4, R * HW, _stream(dev))
+        return dy.to(ctx.in_dtype), None, None, None
+
+
+def lift_splat_logits(y: torch.Tensor, D: int, C: int, plan: Plan,
+                      memory_format: torch.memory_format = torch.channels_last) -> torch.Tensor:
+    """BEV (B, C*Z, X, Y) = splat(lift(softmax(y[:, :D], dim=1), y[:, D:D+C])) for the CamEncode conv
+    output y (B*N, >= D+C, fH, fW); see _LiftSplatLogits."""
+    out = _LiftSplatLogits.apply(y, D, C, plan)
+    if memory_format == torch.contiguous_format:
+        out = out.contiguous()
+    return out
+
+
 # --------------------------------------------------------------------------
 # dense pooling (K4a / K5a): voxel_pooling on a materialised frustum tensor
 # --------------------------------------------------------------------------

@@ -42,6 +42,8 @@ class _ModuleCache:
         self.static = False
         self.plan: Optional[F.Plan] = None
         self.plan_builds = 0
+        # producer fusion: None = not probed yet
+        self.fuse_softmax: Optional[bool] = None
 
 
 def _cache(module) -> _ModuleCache:
@@ -118,6 +120,21 @@ def _split_depth_feat(self, x):
     return depth, feat
 
 
+def _softmax_is_fusable(c: _ModuleCache, ce, like: torch.Tensor) -> bool:
+    """The fused path replaces ``ce.get_depth_dist`` by its own softmax over the D logit channels;
+    that is only allowed when get_depth_dist IS that softmax (reference src/modules.py:76-77).
+    Probed once per module on a small random tensor."""
+    if c.fuse_softmax is None:
+        ok = hasattr(ce, "depthnet") and hasattr(ce, "get_depth_dist") and int(ce.D) <= 128
+        if ok:
+            with torch.no_grad():
+                probe = torch.randn(2, int(ce.D), 2, 3, device=like.device, dtype=torch.float32)
+                got = ce.get_depth_dist(probe)
+                ok = tuple(got.shape) == tuple(probe.shape) and torch.allclose(got, probe.softmax(dim=1), rtol=1e-6, atol=1e-7)
+        c.fuse_softmax = bool(ok)
+    return c.fuse_softmax
+
+
 def get_cam_feats(self, x):
     """Lazy B x N x D x fH x fW x C handle; reference src/model_baseline.py:72-82."""
     BN = x.shape[0]
@@ -149,6 +166,14 @@ def get_voxels(self, x, rots, trans, intrins, post_rots, post_trans):
     reference src/model_baseline.py:128-133."""
     c = _cache(self)
     plan = _plan_for(c, (rots, trans, intrins, post_rots, post_trans))
+    ce = self.camencode
+    if _softmax_is_fusable(c, ce, x):
+        # conv output -> (softmax + split + staging) -> lift+splat; softmax backward fused into K5
+        y = ce.depthnet(x)
+        if y.shape[0] != plan.B * plan.N:
+            raise RuntimeError("get_voxels: %d camera images but calibration for %d x %d"
+                               % (y.shape[0], plan.B, plan.N))
+        return F.lift_splat_logits(y, int(ce.D), int(ce.C), plan)
     depth, feat = _split_depth_feat(self, x)
     if depth.shape[0] != plan.B * plan.N:
         raise RuntimeError("get_voxels: %d camera images but calibration for %d x %d"
