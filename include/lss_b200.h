@@ -55,6 +55,10 @@ typedef enum LssStatus {
 
 typedef enum LssBevLayout { LSS_BEV_NHWC = 0, LSS_BEV_NCHW = 1 } LssBevLayout;
 
+/* dtype of the feature tensors at the boundary (depth / logits / feat in, their gradients out);
+ * arithmetic, the BEV map and dBEV are always float32 */
+typedef enum LssDtype { LSS_F32 = 0, LSS_F16 = 1, LSS_BF16 = 2 } LssDtype;
+
 /* Grid constants, the products of gen_dx_bx (reference src/tools.py:172-178). */
 typedef struct LssGrid {
   float dx[3]; /* voxel size            */
@@ -216,9 +220,11 @@ int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* sh
 /* The same with a batch stride (in elements) per input, so depth and feat may be channel slices of
  * ONE conv output (B*N, D+C, fH, fW) as CamEncode produces it (src/modules.py:74,82-84), and with
  * softmax != 0 the first input holds the depth LOGITS: the depth distribution
- * x[:, :D].softmax(dim=1) (src/modules.py:76-77) is computed while staging (D <= 128). */
-int lss_lift_stage_ex(const float* d_depth_or_logits, int64_t depth_batch_stride, const float* d_feat,
-                      int64_t feat_batch_stride, const LssShape* shape, int32_t softmax,
+ * x[:, :D].softmax(dim=1) (src/modules.py:76-77) is computed while staging (D <= 128).
+ * dtype (LssDtype) is the element type of BOTH inputs (the AMP scripts hand over half tensors,
+ * train_vovnet_transformer.py:196); strides are in elements; the staged copies are float32. */
+int lss_lift_stage_ex(const void* d_depth_or_logits, int64_t depth_batch_stride, const void* d_feat,
+                      int64_t feat_batch_stride, const LssShape* shape, int32_t softmax, int32_t dtype,
                       float* d_depth_t, float* d_feat_t, void* stream);
 
 /* ------------------------------------------------------------------------- *
@@ -238,11 +244,12 @@ int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* 
                       int32_t layout, float* d_ddepth, float* d_dfeat, void* stream);
 /* The same with output batch strides (the two gradients may be channel slices of one tensor) and,
  * with softmax != 0, the softmax backward fused: the first output receives the gradient of the depth
- * LOGITS, p * (d_depth - sum_d p * d_depth), p = d_depth_t (autograd of src/modules.py:77; D <= 128). */
+ * LOGITS, p * (d_depth - sum_d p * d_depth), p = d_depth_t (autograd of src/modules.py:77; D <= 128).
+ * out_dtype (LssDtype) is the element type of both gradient outputs. */
 int lss_liftsplat_bwd_ex(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
                          const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                         int32_t layout, int32_t softmax, float* d_ddepth_or_dlogits,
-                         int64_t ddepth_batch_stride, float* d_dfeat, int64_t dfeat_batch_stride,
+                         int32_t layout, int32_t softmax, int32_t out_dtype, void* d_ddepth_or_dlogits,
+                         int64_t ddepth_batch_stride, void* d_dfeat, int64_t dfeat_batch_stride,
                          void* stream);
 
 #ifdef __cplusplus

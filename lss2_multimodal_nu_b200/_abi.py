@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, LIB_NAME)
 ABI_VERSION = 2
 LSS_BEV_NHWC = 0
 LSS_BEV_NCHW = 1
+LSS_F32, LSS_F16, LSS_BF16 = 0, 1, 2
 
 
 class LssGrid(C.Structure):
@@ -54,10 +55,10 @@ SIGNATURES = {
     "lss_pool_dense_fwd": (C.c_int, [_p, _p, _p, _p, _G, _i32, _i32, _i64, _i32, _p, _p]),
     "lss_pool_dense_bwd": (C.c_int, [_p, _p, _G, _i32, _i32, _i64, _i32, _p, _p]),
     "lss_lift_stage": (C.c_int, [_p, _p, _S, _p, _p, _p]),
-    "lss_lift_stage_ex": (C.c_int, [_p, _i64, _p, _i64, _S, _i32, _p, _p, _p]),
+    "lss_lift_stage_ex": (C.c_int, [_p, _i64, _p, _i64, _S, _i32, _i32, _p, _p, _p]),
     "lss_liftsplat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _G, _S, _i32, _p, _p]),
     "lss_liftsplat_bwd": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _p, _p, _p]),
-    "lss_liftsplat_bwd_ex": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _i32, _p, _i64, _p, _i64, _p]),
+    "lss_liftsplat_bwd_ex": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
     "lss_plan_workspace_bytes": (_sz, [_S, _G]),
     "lss_plan_key_count": (_i64, [_G, _i32]),
     "lss_plan_key_tile": (C.c_int, []),

@@ -125,7 +125,8 @@ static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& 
 
 template <int kLanes>
 static int launch_bwd(const PoolBwdArgs& a, int blocks, cudaStream_t st) {
-  liftsplat_bwd_nhwc_kernel<kLanes><<<blocks, kBwdThreads, 0, st>>>(a);
+  if (a.softmax || a.out_dtype != LSS_F32) liftsplat_bwd_nhwc_kernel<kLanes, true><<<blocks, kBwdThreads, 0, st>>>(a);
+  else liftsplat_bwd_nhwc_kernel<kLanes, false><<<blocks, kBwdThreads, 0, st>>>(a);
   LSS_LAUNCH_CHECK("liftsplat_bwd_nhwc_kernel");
   return LSS_OK;
 }
@@ -323,10 +324,11 @@ int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGri
   return LSS_OK;
 }
 
-static int lift_stage_common(const float* d_depth, long long depth_bs, const float* d_feat, long long feat_bs,
-                             const LssShape* shape, int softmax, float* d_depth_t, float* d_feat_t,
+static int lift_stage_common(const void* d_depth, long long depth_bs, const void* d_feat, long long feat_bs,
+                             const LssShape* shape, int softmax, int dtype, float* d_depth_t, float* d_feat_t,
                              cudaStream_t st) {
   LSS_REQUIRE(d_depth && d_feat && d_depth_t && d_feat_t, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(valid_dtype(dtype), LSS_ERR_UNSUPPORTED);
   int rc = check_shape(shape);
   if (rc) return rc;
   const int HW = shape->fH * shape->fW, BN = shape->B * shape->N;
@@ -336,12 +338,14 @@ static int lift_stage_common(const float* d_depth, long long depth_bs, const flo
   dim3 grid((HW + 31) / 32, (R + 31) / 32, BN * 2);
   if (softmax) {
     LSS_REQUIRE(shape->D <= kSoftmaxMaxD, LSS_ERR_UNSUPPORTED);
-    lift_stage_softmax_kernel<<<dim3((HW + 31) / 32, BN), 256, 0, st>>>(d_depth, depth_bs, shape->D, HW, d_depth_t);
+    lift_stage_softmax_kernel<<<dim3((HW + 31) / 32, BN), 256, 0, st>>>(d_depth, depth_bs, dtype, shape->D, HW,
+                                                                        d_depth_t);
     LSS_LAUNCH_CHECK("lift_stage_softmax_kernel");
-    lift_stage_kernel<<<grid, 256, 0, st>>>(nullptr, 0, d_feat, feat_bs, shape->D, shape->C, HW, d_depth_t, d_feat_t);
-  } else {
-    lift_stage_kernel<<<grid, 256, 0, st>>>(d_depth, depth_bs, d_feat, feat_bs, shape->D, shape->C, HW, d_depth_t,
+    lift_stage_kernel<<<grid, 256, 0, st>>>(nullptr, 0, d_feat, feat_bs, dtype, shape->D, shape->C, HW, d_depth_t,
                                             d_feat_t);
+  } else {
+    lift_stage_kernel<<<grid, 256, 0, st>>>(d_depth, depth_bs, d_feat, feat_bs, dtype, shape->D, shape->C, HW,
+                                            d_depth_t, d_feat_t);
   }
   LSS_LAUNCH_CHECK("lift_stage_kernel");
   return LSS_OK;
@@ -351,15 +355,15 @@ int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* sh
                    float* d_depth_t, float* d_feat_t, void* stream) {
   if (check_shape(shape) != LSS_OK) return check_shape(shape);
   const long long HW = (long long)shape->fH * shape->fW;
-  return lift_stage_common(d_depth, shape->D * HW, d_feat, shape->C * HW, shape, 0, d_depth_t, d_feat_t,
+  return lift_stage_common(d_depth, shape->D * HW, d_feat, shape->C * HW, shape, 0, LSS_F32, d_depth_t, d_feat_t,
                            as_stream(stream));
 }
 
-int lss_lift_stage_ex(const float* d_depth_or_logits, int64_t depth_batch_stride, const float* d_feat,
-                      int64_t feat_batch_stride, const LssShape* shape, int32_t softmax,
+int lss_lift_stage_ex(const void* d_depth_or_logits, int64_t depth_batch_stride, const void* d_feat,
+                      int64_t feat_batch_stride, const LssShape* shape, int32_t softmax, int32_t dtype,
                       float* d_depth_t, float* d_feat_t, void* stream) {
   return lift_stage_common(d_depth_or_logits, depth_batch_stride, d_feat, feat_batch_stride, shape, softmax ? 1 : 0,
-                           d_depth_t, d_feat_t, as_stream(stream));
+                           dtype, d_depth_t, d_feat_t, as_stream(stream));
 }
 
 int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32_t* d_sorted_points,
@@ -377,9 +381,10 @@ int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32
 
 static int liftsplat_bwd_common(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
                                 const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                                int32_t layout, int softmax, float* d_ddepth, long long ddepth_bs,
-                                float* d_dfeat, long long dfeat_bs, cudaStream_t st) {
+                                int32_t layout, int softmax, int out_dtype, void* d_ddepth, long long ddepth_bs,
+                                void* d_dfeat, long long dfeat_bs, cudaStream_t st) {
   LSS_REQUIRE(d_dbev && d_depth_t && d_feat_t && d_cells && d_ddepth && d_dfeat, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(valid_dtype(out_dtype), LSS_ERR_UNSUPPORTED);
   int rc = check_shape(shape);
   if (rc) return rc;
   GridDev g;
@@ -393,7 +398,7 @@ static int liftsplat_bwd_common(const float* d_dbev, const float* d_depth_t, con
   PoolBwdArgs a;
   a.dbev = reinterpret_cast<const float4*>(d_dbev); a.depth_t = d_depth_t;
   a.feat_t = reinterpret_cast<const float4*>(d_feat_t); a.cells = d_cells;
-  a.ddepth = d_ddepth; a.dfeat = d_dfeat; a.ddepth_bs = ddepth_bs; a.dfeat_bs = dfeat_bs; a.softmax = softmax;
+  a.ddepth = d_ddepth; a.dfeat = d_dfeat; a.ddepth_bs = ddepth_bs; a.dfeat_bs = dfeat_bs; a.softmax = softmax; a.out_dtype = out_dtype;
   a.D = shape->D; a.fH = shape->fH; a.fW = shape->fW; a.C = shape->C; a.G = shape->C / 4;
   a.n_pix = shape->B * shape->N * shape->fH * shape->fW;
   a.div_fh = FastDiv((uint32_t)shape->fH); a.div_fw = FastDiv((uint32_t)shape->fW);
@@ -412,17 +417,17 @@ int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* 
                       int32_t layout, float* d_ddepth, float* d_dfeat, void* stream) {
   if (check_shape(shape) != LSS_OK) return check_shape(shape);
   const long long HW = (long long)shape->fH * shape->fW;
-  return liftsplat_bwd_common(d_dbev, d_depth_t, d_feat_t, d_cells, grid, shape, layout, 0, d_ddepth,
+  return liftsplat_bwd_common(d_dbev, d_depth_t, d_feat_t, d_cells, grid, shape, layout, 0, LSS_F32, d_ddepth,
                               shape->D * HW, d_dfeat, shape->C * HW, as_stream(stream));
 }
 
 int lss_liftsplat_bwd_ex(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
                          const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                         int32_t layout, int32_t softmax, float* d_ddepth_or_dlogits,
-                         int64_t ddepth_batch_stride, float* d_dfeat, int64_t dfeat_batch_stride,
+                         int32_t layout, int32_t softmax, int32_t out_dtype, void* d_ddepth_or_dlogits,
+                         int64_t ddepth_batch_stride, void* d_dfeat, int64_t dfeat_batch_stride,
                          void* stream) {
   return liftsplat_bwd_common(d_dbev, d_depth_t, d_feat_t, d_cells, grid, shape, layout, softmax ? 1 : 0,
-                              d_ddepth_or_dlogits, ddepth_batch_stride, d_dfeat, dfeat_batch_stride,
+                              out_dtype, d_ddepth_or_dlogits, ddepth_batch_stride, d_dfeat, dfeat_batch_stride,
                               as_stream(stream));
 }
 

@@ -2,6 +2,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -153,6 +155,19 @@ inline int make_keymap(const GridDev& g, KeyMap* k) {
   k->div_xt = FastDiv((uint32_t)k->XT);
   return LSS_OK;
 }
+
+// ---- feature dtypes at the boundary (LssDtype): arithmetic is always float32 ----
+__device__ __forceinline__ float load_as_float(const void* base, size_t i, int dtype) {
+  if (dtype == LSS_F16) return __half2float(reinterpret_cast<const __half*>(base)[i]);
+  if (dtype == LSS_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
+  return reinterpret_cast<const float*>(base)[i];
+}
+__device__ __forceinline__ void store_from_float(void* base, size_t i, float v, int dtype) {
+  if (dtype == LSS_F16) reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
+  else if (dtype == LSS_BF16) reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(base)[i] = v;
+}
+inline bool valid_dtype(int d) { return d == LSS_F32 || d == LSS_F16 || d == LSS_BF16; }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 

@@ -82,15 +82,16 @@ intervals_kernel(IntervalArgs a) {
 // grid = (ceil(HW/32), ceil(max(D,C)/32), BN * 2)  [z even: depth, odd: feat]
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-lift_stage_kernel(const float* __restrict__ depth, long long depth_bs, const float* __restrict__ feat,
-                  long long feat_bs, int D, int C, int HW, float* __restrict__ depth_t,
+lift_stage_kernel(const void* __restrict__ depth, long long depth_bs, const void* __restrict__ feat,
+                  long long feat_bs, int dtype, int D, int C, int HW, float* __restrict__ depth_t,
                   float* __restrict__ feat_t) {
   __shared__ float tile[32][33];
   const int which = blockIdx.z & 1;
   const int bn = blockIdx.z >> 1;
   const int R = which ? C : D;
   if (!which && depth == nullptr) return;              // depth staged elsewhere (softmax variant)
-  const float* src = which ? feat + (size_t)bn * feat_bs : depth + (size_t)bn * depth_bs;
+  const void* src = which ? feat : depth;
+  const size_t sbase = (size_t)bn * (which ? feat_bs : depth_bs);
   float* dst = (which ? feat_t : depth_t) + (size_t)bn * HW * R;
   const int r0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   if (r0 >= R) return;
@@ -98,7 +99,7 @@ lift_stage_kernel(const float* __restrict__ depth, long long depth_bs, const flo
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int r = r0 + ty + k * 8, p = p0 + tx;
-    tile[ty + k * 8][tx] = (r < R && p < HW) ? src[(size_t)r * HW + p] : 0.0f;
+    tile[ty + k * 8][tx] = (r < R && p < HW) ? load_as_float(src, sbase + (size_t)r * HW + p, dtype) : 0.0f;
   }
   __syncthreads();
 #pragma unroll
@@ -115,17 +116,17 @@ lift_stage_kernel(const float* __restrict__ depth, long long depth_bs, const flo
 // p = exp(x - max) / sum, the expression torch evaluates.
 constexpr int kSoftmaxMaxD = 128;
 __global__ void __launch_bounds__(256)
-lift_stage_softmax_kernel(const float* __restrict__ logits, long long logits_bs, int D, int HW,
+lift_stage_softmax_kernel(const void* __restrict__ logits, long long logits_bs, int dtype, int D, int HW,
                           float* __restrict__ depth_t) {
   __shared__ float tile[kSoftmaxMaxD][33];
   __shared__ float s_max[32], s_inv[32];
   const int bn = blockIdx.y, p0 = blockIdx.x * 32;
-  const float* src = logits + (size_t)bn * logits_bs;
+  const size_t sbase = (size_t)bn * logits_bs;
   float* dst = depth_t + (size_t)bn * HW * D;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int r = ty; r < D; r += 8) {
     const int p = p0 + tx;
-    tile[r][tx] = (p < HW) ? src[(size_t)r * HW + p] : 0.0f;
+    tile[r][tx] = (p < HW) ? load_as_float(logits, sbase + (size_t)r * HW + p, dtype) : 0.0f;
   }
   __syncthreads();
   if (ty == 0) {                                      // one lane per pixel: max, then the sum of exp
@@ -466,9 +467,10 @@ struct PoolBwdArgs {
   const float* depth_t;     // (BN*HW, D)
   const float4* feat_t;     // (BN*HW, G)
   const int32_t* cells;     // (BN, D, fH, fW)
-  float* ddepth;            // (BN, D, fH, fW) with batch stride ddepth_bs: d_depth, or d_logits when softmax
-  float* dfeat;             // (BN, C, fH, fW) with batch stride dfeat_bs
+  void* ddepth;             // (BN, D, fH, fW) with batch stride ddepth_bs: d_depth, or d_logits when softmax
+  void* dfeat;              // (BN, C, fH, fW) with batch stride dfeat_bs
   long long ddepth_bs, dfeat_bs;
+  int out_dtype;            // LssDtype of both outputs
   int softmax;              // 1: depth_t = softmax(logits); emit d_logits = p * (d_depth - sum_d p * d_depth)
   int D, fH, fW, C, G;
   int n_pix;                // BN * fH * fW
@@ -479,7 +481,9 @@ constexpr int kBwdThreads = 256;
 constexpr int kBwdWarps = kBwdThreads / 32;
 constexpr int kBwdChunk = 128;   // depth bins staged per warp at a time
 
-template <int kLanes>
+// kGeneral = false: float32 gradients, no fused softmax (the plain K5); true: output dtype and the
+// fused softmax backward are run-time options (kept out of the plain kernel's inner loop)
+template <int kLanes, bool kGeneral>
 __global__ void __launch_bounds__(kBwdThreads, LSS_BWD_MINB)
 liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
   constexpr int kPts = 32 / kLanes;                 // points per warp step
@@ -489,7 +493,7 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
   constexpr int kLogU = kUnroll == 8 ? 3 : 2;
   static_assert(kBwdChunk % kRound == 0, "chunk must hold whole rounds");
   __shared__ int2 s_cd[kBwdWarps][kBwdChunk];       // {output cell, depth bits} of the staged bins
-  __shared__ float s_dd[kBwdWarps][kBwdChunk];      // d_depth of the pixel (softmax backward needs all of them)
+  __shared__ float s_dd[kGeneral ? kBwdWarps : 1][kGeneral ? kBwdChunk : 1];   // d_depth of the pixel (softmax backward)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // pixel of this warp: h fastest, so a CTA is one image column (bn, w) when fH == 8
@@ -573,12 +577,14 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
       }
       const int d = dc + d0 + my_u * kPts + grp;
       if (writer && d < a.D) {
-        if (a.softmax) s_dd[warp][d] = static_cast<float>(dot[0]);        // D <= kBwdChunk (host)
-        else a.ddepth[(size_t)bn * a.ddepth_bs + (size_t)d * HW + col] = static_cast<float>(dot[0]);
+        const size_t o = (size_t)bn * a.ddepth_bs + (size_t)d * HW + col;
+        if (!kGeneral) reinterpret_cast<float*>(a.ddepth)[o] = static_cast<float>(dot[0]);
+        else if (a.softmax) s_dd[warp][d] = static_cast<float>(dot[0]);   // D <= kBwdChunk (host)
+        else store_from_float(a.ddepth, o, static_cast<float>(dot[0]), a.out_dtype);
       }
     }
   }
-  if (a.softmax) {
+  if (kGeneral && a.softmax) {
     // softmax backward (reference: autograd of x.softmax(dim=1), src/modules.py:77), fused:
     // d_logit[d] = p[d] * (d_depth[d] - sum_d' p[d'] * d_depth[d'])
     __syncwarp();
@@ -588,7 +594,8 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
     for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
     const float spf = static_cast<float>(sp);
     for (int l = lane; l < a.D; l += 32)
-      a.ddepth[(size_t)bn * a.ddepth_bs + (size_t)l * HW + col] = __int_as_float(cd[l].y) * (s_dd[warp][l] - spf);
+      store_from_float(a.ddepth, (size_t)bn * a.ddepth_bs + (size_t)l * HW + col,
+                       __int_as_float(cd[l].y) * (s_dd[warp][l] - spf), a.out_dtype);
   }
   // fold the kPts point-groups of the warp together
 #pragma unroll
@@ -599,8 +606,16 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
     acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
   }
   if (grp == 0 && lane_active) {
-    float* df = a.dfeat + (size_t)bn * a.dfeat_bs + (size_t)(sub * 4) * HW + col;
-    df[0] = acc.x; df[HW] = acc.y; df[2 * (size_t)HW] = acc.z; df[3 * (size_t)HW] = acc.w;
+    const size_t df = (size_t)bn * a.dfeat_bs + (size_t)(sub * 4) * HW + col;
+    if (!kGeneral) {
+      float* o = reinterpret_cast<float*>(a.dfeat) + df;
+      o[0] = acc.x; o[HW] = acc.y; o[2 * (size_t)HW] = acc.z; o[3 * (size_t)HW] = acc.w;
+    } else {
+      store_from_float(a.dfeat, df, acc.x, a.out_dtype);
+      store_from_float(a.dfeat, df + HW, acc.y, a.out_dtype);
+      store_from_float(a.dfeat, df + 2 * (size_t)HW, acc.z, a.out_dtype);
+      store_from_float(a.dfeat, df + 3 * (size_t)HW, acc.w, a.out_dtype);
+    }
   }
 }
 

@@ -56,6 +56,24 @@ def _need_cuda(*tensors: torch.Tensor) -> torch.device:
     return dev
 
 
+_DTYPES = {torch.float32: _abi.LSS_F32, torch.float16: _abi.LSS_F16, torch.bfloat16: _abi.LSS_BF16}
+
+
+def _batch_dense(t: torch.Tensor) -> bool:
+    """True when every batch item of a (BN, R, H, W) tensor is dense (only the batch stride is free),
+    i.e. the tensor is contiguous or a channel slice of a contiguous conv output."""
+    BN, R, H, W = t.shape
+    return t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W and t.stride(0) >= R * H * W
+
+
+def _feature_input(t: torch.Tensor) -> torch.Tensor:
+    """A feature tensor the staging kernel can read in place: float32 / float16 / bfloat16, dense per
+    batch item.  Anything else is converted / copied."""
+    if t.dtype not in _DTYPES:
+        t = t.float()
+    return t if _batch_dense(t) else t.contiguous()
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     """float32 + contiguous (no copy when already so)."""
     if t.dtype != torch.float32:
@@ -351,16 +369,21 @@ def _as_nhwc(grad: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # fused lift + splat (K4 / K5)
 # --------------------------------------------------------------------------
-def lift_stage(depth: torch.Tensor, feat: torch.Tensor, plan: Plan):
-    """Pixel-major staging copies (B*N*fH*fW, D) and (B*N*fH*fW, C)."""
+def lift_stage(depth: torch.Tensor, feat: torch.Tensor, plan: Plan, softmax: bool = False):
+    """Pixel-major float32 staging copies (B*N*fH*fW, D) and (B*N*fH*fW, C).  depth / feat may be
+    float32, float16 or bfloat16 (the AMP scripts hand over half tensors) and channel slices of one
+    conv output; with ``softmax`` the first tensor holds logits and the copy holds softmax over D."""
     dev = _need_cuda(depth, feat)
-    depth, feat = _f32c(depth), _f32c(feat)
+    if depth.dtype != feat.dtype:
+        common = torch.promote_types(depth.dtype, feat.dtype)
+        depth, feat = depth.to(common), feat.to(common)
+    depth, feat = _feature_input(depth), _feature_input(feat)
     BN, C = feat.shape[0], feat.shape[1]
     HW = plan.fH * plan.fW
     depth_t = torch.empty((BN * HW, plan.D), dtype=torch.float32, device=dev)
     feat_t = torch.empty((BN * HW, C), dtype=torch.float32, device=dev)
-    _abi.call("lss_lift_stage", _ptr(depth), _ptr(feat), plan.shape(C), _ptr(depth_t),
-              _ptr(feat_t), _stream(dev))
+    _abi.call("lss_lift_stage_ex", _ptr(depth), depth.stride(0), _ptr(feat), feat.stride(0), plan.shape(C),
+              1 if softmax else 0, _DTYPES[depth.dtype], _ptr(depth_t), _ptr(feat_t), _stream(dev))
     return depth_t, feat_t
 
 
@@ -397,12 +420,15 @@ class _LiftSplat(torch.autograd.Function):
         plan, C = ctx.plan, ctx.C
         dev = grad_bev.device
         g = _as_nhwc(grad_bev)
-        ddepth = torch.empty((plan.B * plan.N, plan.D, plan.fH, plan.fW), dtype=torch.float32, device=dev)
-        dfeat = torch.empty((plan.B * plan.N, C, plan.fH, plan.fW), dtype=torch.float32, device=dev)
-        _abi.call("lss_liftsplat_bwd", _ptr(g), _ptr(depth_t), _ptr(feat_t), _ptr(plan.cells),
-                  plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC, _ptr(ddepth), _ptr(dfeat),
-                  _stream(dev))
-        return ddepth.to(ctx.in_dtypes[0]), dfeat.to(ctx.in_dtypes[1]), None
+        dt_d, dt_f = ctx.in_dtypes
+        out_dt = dt_d if (dt_d == dt_f and dt_d in _DTYPES) else torch.float32
+        BN, HW = plan.B * plan.N, plan.fH * plan.fW
+        ddepth = torch.empty((BN, plan.D, plan.fH, plan.fW), dtype=out_dt, device=dev)
+        dfeat = torch.empty((BN, C, plan.fH, plan.fW), dtype=out_dt, device=dev)
+        _abi.call("lss_liftsplat_bwd_ex", _ptr(g), _ptr(depth_t), _ptr(feat_t), _ptr(plan.cells),
+                  plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC, 0, _DTYPES[out_dt], _ptr(ddepth),
+                  plan.D * HW, _ptr(dfeat), C * HW, _stream(dev))
+        return ddepth.to(dt_d), dfeat.to(dt_f), None
 
 
 def lift_splat(depth: torch.Tensor, feat: torch.Tensor, plan: Plan,
@@ -419,14 +445,6 @@ def lift_splat(depth: torch.Tensor, feat: torch.Tensor, plan: Plan,
     if memory_format == torch.contiguous_format:
         out = out.contiguous()
     return out
-
-
-def _batch_strided(t: torch.Tensor) -> bool:
-    """True when every batch item of a (BN, R, H, W) tensor is dense (only the batch stride is free),
-    i.e. the tensor is a channel slice of a contiguous conv output."""
-    BN, R, H, W = t.shape
-    return t.dtype == torch.float32 and t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W \
-        and t.stride(0) >= R * H * W
 
 
 class _LiftSplatLogits(torch.autograd.Function):
@@ -446,13 +464,12 @@ class _LiftSplatLogits(torch.autograd.Function):
             raise RuntimeError("conv output %s does not match D=%d C=%d and the plan (B=%d N=%d D=%d fH=%d fW=%d)"
                                % (tuple(y.shape), D, C, plan.B, plan.N, plan.D, plan.fH, plan.fW))
         ctx.in_dtype = y.dtype
-        y32 = y if _batch_strided(y) else _f32c(y)
+        yy = _feature_input(y)
         HW = fH * fW
         depth_t = torch.empty((BN * HW, D), dtype=torch.float32, device=dev)
         feat_t = torch.empty((BN * HW, C), dtype=torch.float32, device=dev)
-        esz = 4
-        _abi.call("lss_lift_stage_ex", y32.data_ptr(), y32.stride(0), y32.data_ptr() + D * HW * esz,
-                  y32.stride(0), plan.shape(C), 1, _ptr(depth_t), _ptr(feat_t), _stream(dev))
+        _abi.call("lss_lift_stage_ex", yy.data_ptr(), yy.stride(0), yy.data_ptr() + D * HW * yy.element_size(),
+                  yy.stride(0), plan.shape(C), 1, _DTYPES[yy.dtype], _ptr(depth_t), _ptr(feat_t), _stream(dev))
         bev = _alloc_bev(plan, C, dev)
         _abi.call("lss_liftsplat_fwd", _ptr(depth_t), _ptr(feat_t), _ptr(plan.sorted_points),
                   _ptr(plan.sorted_cells), _ptr(plan.key_start), plan.grid.c(), plan.shape(C),
@@ -468,10 +485,11 @@ class _LiftSplatLogits(torch.autograd.Function):
         dev = grad_bev.device
         g = _as_nhwc(grad_bev)
         BN, HW = plan.B * plan.N, plan.fH * plan.fW
-        dy = (torch.zeros if R > D + C else torch.empty)((BN, R, plan.fH, plan.fW), dtype=torch.float32, device=dev)
+        out_dt = ctx.in_dtype if ctx.in_dtype in _DTYPES else torch.float32
+        dy = (torch.zeros if R > D + C else torch.empty)((BN, R, plan.fH, plan.fW), dtype=out_dt, device=dev)
         _abi.call("lss_liftsplat_bwd_ex", _ptr(g), _ptr(depth_t), _ptr(feat_t), _ptr(plan.cells),
-                  plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC, 1, dy.data_ptr(), R * HW,
-                  dy.data_ptr() + D * HW * 4, R * HW, _stream(dev))
+                  plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC, 1, _DTYPES[out_dt], dy.data_ptr(), R * HW,
+                  dy.data_ptr() + D * HW * dy.element_size(), R * HW, _stream(dev))
         return dy.to(ctx.in_dtype), None, None, None
 
 

@@ -569,3 +569,35 @@ def test_fused_softmax_matches_unfused_path(golden_dir, extra):
     geom = O.get_geometry(g["frustum"], **{k: g[k] for k in CAL})
     want, _ = O.voxel_pooling(geom, x64, g["dx"], g["bx"], g["nx"], g["trans"].shape[0], mode="exact")
     close(cpu(bev1), want, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_io(golden_dir, dtype):
+    """half depth / feat are read in place (no up-cast copy), arithmetic stays float32,
+    gradients come back in the input dtype."""
+    g = load(golden_dir, "tiny")
+    us, vs, ds = axes_of(g)
+    plan = F.build_plan(us, vs, ds, *(dev(g[k]) for k in CAL), grid_of(g))
+    depth_h = dev(g["depth"]).to(dtype); feat_h = dev(g["feat"]).to(dtype)
+    d1 = depth_h.clone().requires_grad_(True); f1 = feat_h.clone().requires_grad_(True)
+    bev = F.lift_splat(d1, f1, plan)
+    assert bev.dtype == torch.float32
+    # reference: the same half values, up-cast, through the float32 path
+    d2 = depth_h.float().requires_grad_(True); f2 = feat_h.float().requires_grad_(True)
+    ref = F.lift_splat(d2, f2, plan)
+    assert torch.equal(bev, ref)
+    gout = dev(g["dbev"])
+    bev.backward(gout); ref.backward(gout)
+    assert d1.grad.dtype == dtype and f1.grad.dtype == dtype
+    assert torch.equal(d1.grad, d2.grad.to(dtype)) and torch.equal(f1.grad, f2.grad.to(dtype))
+    # logits path with half conv output
+    BN, D, fH, fW = g["depth"].shape
+    C = g["feat"].shape[1]
+    y = (torch.randn(BN, D + C, fH, fW, device=DEV) * 2).to(dtype)
+    y1 = y.clone().requires_grad_(True)
+    b1 = F.lift_splat_logits(y1, D, C, plan)
+    y2 = y.float().requires_grad_(True)
+    b2 = F.lift_splat_logits(y2, D, C, plan)
+    assert torch.equal(b1, b2)
+    b1.backward(gout); b2.backward(gout)
+    assert y1.grad.dtype == dtype and torch.equal(y1.grad, y2.grad.to(dtype))
