@@ -477,7 +477,10 @@ struct PoolBwdArgs {
   FastDiv div_fh, div_fw;
 };
 
-constexpr int kBwdThreads = 256;
+#ifndef LSS_BWD_THREADS
+#define LSS_BWD_THREADS 256
+#endif
+constexpr int kBwdThreads = LSS_BWD_THREADS;
 constexpr int kBwdWarps = kBwdThreads / 32;
 constexpr int kBwdChunk = 128;   // depth bins staged per warp at a time
 
