@@ -5,12 +5,14 @@
 
 One "step" = one batch (B=8 samples x 6 cameras, 128x352, D=41, C=64, 200x200x1
 BEV) through the whole hot path, forward + backward:
-    camera prep + frustum geometry -> ranks -> radix sort -> intervals   (lss_build_plan)
+    camera prep + frustum geometry -> keys -> counting sort -> intervals  (lss_build_plan)
     lift staging -> fused lift+splat forward                            (lss_lift_stage, lss_liftsplat_fwd)
     fused backward                                                       (lss_liftsplat_bwd)
-`value`   device-resident inputs, every step replayed as a CUDA graph of the C-ABI calls.
-`e2e`     the public Python API (functional.build_plan + lift_splat autograd) fed from pinned
-          HOST buffers: H2D of depth/feat/calibration and D2H of the gradients every step.
+`value`   device-resident inputs, every step replayed as ONE CUDA graph of the C-ABI calls, rotating batch
+          sets larger than L2, `--in-flight` (default 4) independent batches in flight, one stream each.
+`serial`  the same steps strictly one after the other (one batch in flight).
+`e2e`     pipeline.HostPipeline (the public API for fixed shapes) fed from pinned HOST buffers: H2D of
+          depth/feat/calibration and D2H of the gradients every step, six steps in flight.
 `roofline` the dominant kernel (fused forward: it writes the whole BEV map), timed alone with CUDA
           events, algorithmic bytes fwd = in + bev.
 `cpu_baseline` / `--impl reference`: the C restatement of the reference's algorithm

@@ -159,10 +159,13 @@ lift_stage_softmax_kernel(const void* __restrict__ logits, long long logits_bs, 
 // neighbours in the list are neighbours on the map.  Every output element is
 // written exactly once (this is the torch.zeros + index_put + cat of reference
 // src/model_baseline.py:120-124) by two kinds of CTAs that run side by side:
-//   * FILL CTAs stream zeros into the empty voxels (75 % of the map at the
-//     headline config): a warp reads the 33 interval bounds of 32 consecutive
-//     cells with one coalesced load (the next block's are prefetched) and covers
-//     the empty lines with 128-bit stores;
+//   * FILL CTAs (one per SM) stream zeros into the empty voxels (75 % of the map
+//     at the headline config): a warp reads the 33 interval bounds of 32
+//     consecutive keys with one coalesced load (the next block's are prefetched)
+//     and every run of empty voxels inside a tile row -- a contiguous piece of
+//     the map -- leaves as ONE bulk async store (TMA engine, cp.async.bulk
+//     shared -> global from a 2 KB zero block), so the zero stream costs the SM
+//     neither issue slots nor load/store queue entries;
 //   * REDUCE CTAs do the warp-level segmented reduction over the sorted point
 //     list.  A warp takes 32 consecutive sorted points -- the unit of work is the
 //     POINT, so dense and sparse regions of the map cost the same -- and owns
