@@ -226,6 +226,9 @@ __device__ __forceinline__ void vec_fma(float d, const float4& f, float4& a) {
 #ifndef LSS_FWD_STAGES
 #define LSS_FWD_STAGES 4
 #endif
+#ifndef LSS_FWD_STAGES4
+#define LSS_FWD_STAGES4 2
+#endif
 #ifndef LSS_BWD_MINB
 #define LSS_BWD_MINB 4
 #endif
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(kPoolThreads, LSS_FWD_MINB)
 pool_fwd_nhwc_kernel(PoolFwdArgs a) {
   using V = typename VecOf<kVec>::type;
   constexpr int kU = 4;                                      // gathers per pipeline stage
-  constexpr int kS = kVec == 4 ? 2 : LSS_FWD_STAGES;         // stages: (kS - 1) * kU gathers in flight
+  constexpr int kS = kVec == 4 ? LSS_FWD_STAGES4 : LSS_FWD_STAGES;   // stages: (kS - 1) * kU gathers in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) phase_stamp_any(2, warp * 2);
 
