@@ -601,3 +601,46 @@ def test_half_precision_io(golden_dir, dtype):
     assert torch.equal(b1, b2)
     b1.backward(gout); b2.backward(gout)
     assert y1.grad.dtype == dtype and torch.equal(y1.grad, y2.grad.to(dtype))
+
+
+ODD_SHAPES = [
+    # name, B, N, final_dim, dbound, xbound, ybound, zbound, C
+    ("c4_grid30x27x3", 2, 3, (64, 112), (4.0, 37.0, 1.5), (-30.0, 30.0, 2.0), (-27.0, 27.0, 2.0), (-6.0, 6.0, 4.0), 4),
+    ("c16_grid17x41", 1, 6, (48, 80), (2.0, 45.0, 1.0), (-34.0, 34.0, 4.0), (-41.0, 41.0, 2.0), (-10.0, 10.0, 20.0), 16),
+    ("c32_grid64x9x2", 3, 2, (32, 208), (4.0, 30.0, 0.5), (-32.0, 32.0, 1.0), (-9.0, 9.0, 2.0), (-4.0, 4.0, 4.0), 32),
+    ("c48_grid100x100", 2, 6, (64, 176), (4.0, 45.0, 1.0), (-50.0, 50.0, 1.0), (-50.0, 50.0, 1.0), (-10.0, 10.0, 20.0), 48),
+    ("c128_dense_runs", 1, 6, (128, 352), (4.0, 45.0, 1.0), (-48.0, 48.0, 8.0), (-48.0, 48.0, 8.0), (-10.0, 10.0, 20.0), 128),
+]
+
+
+@pytest.mark.parametrize("spec", ODD_SHAPES, ids=[s[0] for s in ODD_SHAPES])
+def test_odd_shapes_against_oracle(spec):
+    """Grids that are no multiple of the key tile (keys without a cell), Z > 1, every lane layout of the
+    kernels (C = 4 ... 128), long runs (coarse grid: hundreds of points per voxel), ragged point counts."""
+    name, B, N, final_dim, dbound, xb, yb, zb, C = spec
+    cfg = S.LSSConfig(name, B=B, N=N, final_dim=final_dim, dbound=dbound, xbound=xb, ybound=yb, zbound=zb, C=C)
+    cal, ft, dbev, axes, grid = _run_config(cfg, seed=99)
+    fr = O.create_frustum(cfg.final_dim, cfg.downsample, cfg.dbound)
+    dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    geom = O.get_geometry(fr, **cal)
+    ip = O.index_pipeline(geom, dx, bx, nx, cfg.B)
+    plan = F.build_plan(*axes, *(dev(cal[k]) for k in CAL), grid)
+    K = len(ip["ranks"])
+    assert K > 0 and cpu(plan.counts).tolist() == [K, len(ip["interval_start"])]
+    check_plan_tables(plan, ip["sorted_point"])
+    assert (cpu(plan.reference_order()) == ip["sorted_point"]).all()
+    depth = dev(ft["depth"]).requires_grad_(True); feat = dev(ft["feat"]).requires_grad_(True)
+    bev = F.lift_splat(depth, feat, plan)
+    bev.backward(dev(dbev))
+    want, _ = O.voxel_pooling(geom, O.lift(ft["depth"].astype(np.float64), ft["feat"].astype(np.float64)),
+                              dx, bx, nx, cfg.B, mode="exact")
+    # long runs sum hundreds of terms: the absolute bar scales with the magnitude of the sum
+    scale = max(1.0, float(np.abs(want).max()))
+    close(cpu(bev), want, rtol=1e-5, atol=1e-6 * scale)
+    dd, df = O.voxel_pooling_backward(dbev, ip, ft["depth"], ft["feat"], nx, cfg.B)
+    close(cpu(depth.grad), dd)
+    close(cpu(feat.grad), df, rtol=1e-5, atol=1e-6 * max(1.0, float(np.abs(df).max())))
+    # dense-x operator on the same plan
+    x = (depth.detach().unsqueeze(1) * feat.detach().unsqueeze(2)).view(
+        cfg.B, cfg.N, C, cfg.D, cfg.fH, cfg.fW).permute(0, 1, 3, 4, 5, 2)
+    close(cpu(F.pool_dense(x, F.plan_from_geom(dev(geom), grid))), want, rtol=1e-5, atol=2e-6 * scale)
