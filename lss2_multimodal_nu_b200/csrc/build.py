@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 SOURCES = ["lss_abi.cu"]
-HEADERS = ["lss_common.cuh", "lss_geometry.cuh", "lss_sort.cuh", "lss_sort_small.cuh", "lss_plan.cuh", "lss_pool.cuh"]
+HEADERS = ["lss_common.cuh", "lss_geometry.cuh", "lss_sort.cuh", "lss_plan.cuh", "lss_pool.cuh"]
 OUT = os.path.join(PKG, "liblss_b200.so")
 
 

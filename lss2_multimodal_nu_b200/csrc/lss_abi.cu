@@ -5,7 +5,6 @@
 #include "lss_geometry.cuh"
 #include "lss_pool.cuh"
 #include "lss_sort.cuh"
-#include "lss_sort_small.cuh"
 #include "lss_plan.cuh"
 
 namespace lss {
@@ -229,10 +228,6 @@ int lss_sort_ranks(const int32_t* d_ranks, int64_t P, int32_t n_cells, int32_t* 
   LSS_REQUIRE(workspace_bytes >= s.total_bytes, LSS_ERR_WORKSPACE_TOO_SMALL);
   cudaStream_t st = as_stream(stream);
   char* w = static_cast<char*>(d_workspace);
-  if (s.small) {
-    LSS_CUDA_TRY(cudaMemsetAsync(w + s.off_flags, 0, s.total_bytes - s.off_flags, st), "memset sort flags");
-    return run_sort_passes_small(s, d_ranks, d_sorted_ranks, d_sorted_points, P, d_workspace, nullptr, st);
-  }
   LSS_CUDA_TRY(cudaMemsetAsync(w + s.off_control, 0, s.control_bytes, st), "memset sort control");
   SortDigits sd = sort_digits(s, d_workspace);
   long long blocks = (P + 256 * 8 - 1) / (256 * 8);

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256)
 lift_stage_softmax_kernel(const void* __restrict__ logits, long long logits_bs, int dtype, int D, int HW,
                           float* __restrict__ depth_t) {
   __shared__ float tile[kSoftmaxMaxD][33];
-  __shared__ float s_max[32], s_inv[32];
+  __shared__ float s_inv[32];
   const int bn = blockIdx.y, p0 = blockIdx.x * 32;
   const size_t sbase = (size_t)bn * logits_bs;
   float* dst = depth_t + (size_t)bn * HW * D;
@@ -138,7 +138,6 @@ lift_stage_softmax_kernel(const void* __restrict__ logits, long long logits_bs, 
       tile[r][tx] = e;
       sum += e;
     }
-    s_max[tx] = m;
     s_inv[tx] = sum;
   }
   __syncthreads();

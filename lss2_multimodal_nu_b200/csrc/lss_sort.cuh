@@ -8,7 +8,9 @@
 // is ranked inside the CTA with warp match_any multi-split (stable by
 // construction: warp-striped loads keep ascending point order), tiles chain
 // their per-digit counts through a decoupled look-back on a status array, and
-// keys + payloads are scattered straight to their final slot of the pass.  The
+// keys + payloads are scattered straight to their final slot of the pass (tiles
+// take tickets, so every tile a CTA waits for has started: no co-residency
+// assumption).  The
 // digit histograms of all passes come from whoever produced the keys (K1/K1'
 // accumulate them on the fly) or from histogram_kernel below.
 #pragma once
@@ -38,20 +40,12 @@ struct SortPlan {
   int bits[4];
   int shift[4];
   long long tiles;
-  bool small;  // single-wave kernel (lss_sort_small.cuh) instead of the chained look-back
   // workspace layout (byte offsets)
   size_t off_tmp_keys, off_tmp_vals, off_control, off_hist, off_ticket, off_status[4];
-  size_t off_flags, off_ctl;  // single-wave control words
   size_t control_bytes, total_bytes;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// Tiles at or below this count run the single-wave kernel (lss_sort_small.cuh),
-// which sorts at most 10 bits per pass (1024 bins keep its per-warp counters in
-// 48 KB of static shared memory).
-constexpr int kSmallMaxTilesPlan = 128;
-constexpr int kSmallMaxBitsPlan = 10;
 
 inline SortPlan make_sort_plan(long long P, int32_t n_cells) {
   SortPlan s;
@@ -62,9 +56,7 @@ inline SortPlan make_sort_plan(long long P, int32_t n_cells) {
   s.key_bits = kb;
   s.tiles = (P + kSortTile - 1) / kSortTile;
   if (s.tiles < 1) s.tiles = 1;
-  s.small = s.tiles <= kSmallMaxTilesPlan;
-  const int max_bits = s.small ? kSmallMaxBitsPlan : kSortMaxBits;
-  s.passes = (kb + max_bits - 1) / max_bits;
+  s.passes = (kb + kSortMaxBits - 1) / kSortMaxBits;
   const int base = kb / s.passes, rem = kb % s.passes;
   int sh = 0;
   for (int i = 0; i < s.passes; ++i) {
@@ -76,18 +68,11 @@ inline SortPlan make_sort_plan(long long P, int32_t n_cells) {
   s.off_tmp_keys = off; off += align_up((size_t)P * 4, 256);
   s.off_tmp_vals = off; off += align_up((size_t)P * 4, 256);
   s.off_control = off;
-  if (s.small) {
-    // rows [tiles][1024] u16 | flags [tiles] u32 | ctl
-    off += align_up((size_t)s.tiles * (1u << kSmallMaxBitsPlan) * 2, 256);
-    s.off_flags = off; off += align_up((size_t)s.tiles * 4, 256);
-    s.off_ctl = off; off += 256;
-  } else {
-    s.off_hist = off; off += (size_t)4 * kSortMaxBins * 4;
-    s.off_ticket = off; off += 256;
-    for (int i = 0; i < s.passes; ++i) {
-      s.off_status[i] = off;
-      off += align_up((size_t)s.tiles * (size_t)(1 << s.bits[i]) * 4, 256);
-    }
+  s.off_hist = off; off += (size_t)4 * kSortMaxBins * 4;
+  s.off_ticket = off; off += 256;
+  for (int i = 0; i < s.passes; ++i) {
+    s.off_status[i] = off;
+    off += align_up((size_t)s.tiles * (size_t)(1 << s.bits[i]) * 4, 256);
   }
   s.control_bytes = off - s.off_control;
   s.total_bytes = off;
