@@ -6,7 +6,7 @@
 One "step" = one batch (B=8 samples x 6 cameras, 128x352, D=41, C=64, 200x200x1
 BEV) through the whole hot path, forward + backward:
     camera prep + frustum geometry -> keys -> counting sort -> intervals  (lss_build_plan)
-    lift staging -> fused lift+splat forward                            (lss_lift_stage, lss_liftsplat_fwd)
+    feature staging -> fused lift+splat forward                         (lss_feat_stage, lss_liftsplat_fwd)
     fused backward                                                       (lss_liftsplat_bwd)
 `value`   device-resident inputs, every step replayed as ONE CUDA graph of the C-ABI calls, rotating batch
           sets larger than L2, `--in-flight` (default 4) independent batches in flight, one stream each.

@@ -26,10 +26,11 @@
  *     held in int32; points that fail the bounds test (:99-101) carry the
  *     sentinel rank n_cells = nx0*nx1*nx2*B, so they sort behind every kept
  *     point.  n_cells must be < 2^31 - 1 and P < 2^31;
- *   - BEV tensors are addressed through LssBevLayout: LSS_BEV_NHWC stores the
- *     logical (B, C*Z, X, Y) result with channels innermost (torch
- *     channels_last strides), LSS_BEV_NCHW is the reference's contiguous layout
- *     (src/model_baseline.py:120-124).  Channel index = z*C + c in both.
+ *   - BEV tensors (d_bev, d_dbev) hold the logical (B, C*Z, X, Y) map of
+ *     src/model_baseline.py:120-124 with channels innermost, i.e. (B, X, Y, Z*C)
+ *     storage = torch channels_last strides; channel index = z*C + c.  One voxel
+ *     is one contiguous line of C floats (128-bit vector access over C).  The
+ *     reference's contiguous NCHW buffer is one transpose away (host wrapper).
  */
 #ifndef LSS_B200_H_
 #define LSS_B200_H_
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define LSS_ABI_VERSION 2
+#define LSS_ABI_VERSION 3
 
 typedef enum LssStatus {
   LSS_OK = 0,
@@ -52,8 +53,6 @@ typedef enum LssStatus {
   LSS_ERR_UNSUPPORTED = -5,
   LSS_ERR_CUDA = -6
 } LssStatus;
-
-typedef enum LssBevLayout { LSS_BEV_NHWC = 0, LSS_BEV_NCHW = 1 } LssBevLayout;
 
 /* dtype of the feature tensors at the boundary (depth / logits / feat in, their gradients out);
  * arithmetic, the BEV map and dBEV are always float32 */
@@ -152,7 +151,8 @@ int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid,
  * lists (K0 -> K1' -> sort -> intervals) in one call, i.e. the geometry half of
  * get_voxels (src/model_baseline.py:128-131) + the argsort of :110 + the
  * interval detection of src/tools.py:196-197.  The plan depends only on the
- * calibration, so evaluation code can build it once per rig and reuse it.
+ * calibration, so evaluation code can build it once per rig and reuse it, and
+ * training code can build it while the image backbone runs.
  *
  * The sort key is the OUTPUT CELL in tile-major order: the BEV plane of every
  * sample is cut into T x T tiles (T = lss_plan_key_tile() = 8) and
@@ -165,92 +165,92 @@ int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid,
  * n_keys = lss_plan_key_count(grid, B) = B*XT*YT*T*T*Z >= n_cells.
  *   d_cells         (P)          output cell ((b*X + x)*Y + y)*Z + z of every point, -1 if it
  *                                fails the bounds test
- *   d_key_start     (n_keys+1)   key k owns d_sorted_points[d_key_start[k] .. d_key_start[k+1]);
+ *   d_key_start     (n_keys+1)   key k owns d_sorted_rec[d_key_start[k] .. d_key_start[k+1]);
  *                                equal bounds = empty voxel; d_key_start[n_keys] = K.
  *                                This table is the interval detection (K3).
- *   d_sorted_points (P)          point ids ordered by (key, point id); first K entries valid
- *   d_sorted_cells  (P)          output cell of each sorted point; -1 beyond the K kept points
+ *   d_sorted_rec    (P,2)        {output cell, point id} ordered by (key, point id): column 1 of
+ *                                the first K rows is nonzero(kept)[argsort] regrouped by key,
+ *                                column 0 the voxel each sorted point falls into; rows beyond the
+ *                                K kept points are {-1, 0}.  16-byte aligned.
  *   d_counts        (2)          {K kept points, V occupied voxels}
- *   workspace: lss_plan_workspace_bytes(shape, grid) bytes, 16-byte aligned, ZERO-FILLED
- *   before first use; a successful call leaves its control part zero again.
+ *   workspace: lss_plan_workspace_bytes(shape, grid) bytes, 16-byte aligned; its first
+ *   lss_plan_workspace_control_bytes(shape, grid) bytes must be ZERO before the first use
+ *   and a successful call leaves them zero again.
  * lss_build_plan_from_geom is the same from a materialised geometry tensor d_geom
  * (P,3) (the literal voxel_pooling(geom_feats, x) signature, src/model_baseline.py:84).
  * ------------------------------------------------------------------------- */
 size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid);
+size_t lss_plan_workspace_control_bytes(const LssShape* shape, const LssGrid* grid);
 int64_t lss_plan_key_count(const LssGrid* grid, int32_t B);
 int lss_plan_key_tile(void);
 int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
                    const float* d_trans, const float* d_intrins, const float* d_post_rots,
                    const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
-                   int32_t* d_cells, int32_t* d_key_start, int32_t* d_sorted_points,
-                   int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace, size_t workspace_bytes,
-                   void* stream);
+                   int32_t* d_cells, int32_t* d_key_start, int32_t* d_sorted_rec, int32_t* d_counts,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
 size_t lss_plan_from_geom_workspace_bytes(int64_t P, const LssGrid* grid, int32_t B);
 int lss_build_plan_from_geom(const float* d_geom, const LssGrid* grid, int32_t B, int64_t P,
-                             int32_t* d_cells, int32_t* d_key_start, int32_t* d_sorted_points,
-                             int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace,
-                             size_t workspace_bytes, void* stream);
+                             int32_t* d_cells, int32_t* d_key_start, int32_t* d_sorted_rec, int32_t* d_counts,
+                             void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K4a dense pooling.  Replaces x[kept][sorts] -> QuickCumsum -> zeros ->
  *     index_put -> cat(unbind) (src/model_baseline.py:102-124) for a
  *     materialised frustum tensor d_x (P,C), given a plan.  Every output element
- *     is written (zeros for empty voxels); d_bev is (B, C*Z, X, Y) in `layout`.
- *     C <= 128.
+ *     is written (zeros for empty voxels).  C <= 128, P * C/4 < 2^31.
  *     Backward (QuickCumsum.backward src/tools.py:211-218 + index backward):
  *     d_dx[p,:] = d_dbev[cell(p),:] for kept points, 0 otherwise.
  * ------------------------------------------------------------------------- */
-int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
-                       const int32_t* d_key_start, const LssGrid* grid, int32_t B, int32_t C, int64_t P,
-                       int32_t layout, float* d_bev, void* stream);
+int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_rec, const int32_t* d_key_start,
+                       const LssGrid* grid, int32_t B, int32_t C, int64_t P, float* d_bev, void* stream);
 int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGrid* grid,
-                       int32_t B, int32_t C, int64_t P, int32_t layout, float* d_dx,
-                       void* stream);
+                       int32_t B, int32_t C, int64_t P, float* d_dx, void* stream);
 
 /* ------------------------------------------------------------------------- *
- * Lift staging: pixel-major copies of the per-pixel depth distribution and
- *     context vector, d_depth (BN,D,fH,fW) -> d_depth_t (BN*fH*fW, D) and
- *     d_feat (BN,C,fH,fW) -> d_feat_t (BN*fH*fW, C).  These (3.5 MB at the
- *     headline config) replace the (B*N,C,D,fH,fW) outer product of
- *     src/modules.py:84 and the permute/reshape copies of
- *     src/model_baseline.py:79-80,89.
+ * Lift staging.  The (B*N,C,D,fH,fW) outer product of src/modules.py:84 and the
+ *     permute/reshape copies of src/model_baseline.py:79-80,89 are never formed.
+ *     What the pooling kernels need instead:
+ *     - the context features with one contiguous row per pixel:
+ *       lss_feat_stage: d_feat (BN,C,fH,fW) -> d_feat_t (BN*fH*fW, C) float32
+ *       (2.2 MB at the headline config).  `feat_batch_stride` (elements) lets the
+ *       input be a channel slice of ONE conv output (B*N, D+C, fH, fW) as
+ *       CamEncode produces it (src/modules.py:74,82-84); `dtype` (LssDtype) is its
+ *       element type (the AMP scripts hand over half tensors,
+ *       train_vovnet_transformer.py:196);
+ *     - the depth distribution indexed by POINT id, which is its native layout
+ *       (BN, D, fH*fW): it is read IN PLACE (any LssDtype, batch stride);
+ *     - only when the distribution still has to be computed from logits:
+ *       lss_depth_softmax: d_logits (BN, D, fH, fW) (batch stride, dtype) ->
+ *       d_depth (BN, D, fH*fW) float32 = x[:, :D].softmax(dim=1), src/modules.py:76-77.
  * ------------------------------------------------------------------------- */
-int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* shape,
-                   float* d_depth_t, float* d_feat_t, void* stream);
-/* The same with a batch stride (in elements) per input, so depth and feat may be channel slices of
- * ONE conv output (B*N, D+C, fH, fW) as CamEncode produces it (src/modules.py:74,82-84), and with
- * softmax != 0 the first input holds the depth LOGITS: the depth distribution
- * x[:, :D].softmax(dim=1) (src/modules.py:76-77) is computed while staging (D <= 128).
- * dtype (LssDtype) is the element type of BOTH inputs (the AMP scripts hand over half tensors,
- * train_vovnet_transformer.py:196); strides are in elements; the staged copies are float32. */
-int lss_lift_stage_ex(const void* d_depth_or_logits, int64_t depth_batch_stride, const void* d_feat,
-                      int64_t feat_batch_stride, const LssShape* shape, int32_t softmax, int32_t dtype,
-                      float* d_depth_t, float* d_feat_t, void* stream);
+int lss_feat_stage(const void* d_feat, int64_t feat_batch_stride, const LssShape* shape, int32_t dtype,
+                   float* d_feat_t, void* stream);
+int lss_depth_softmax(const void* d_logits, int64_t logits_batch_stride, const LssShape* shape, int32_t dtype,
+                      float* d_depth, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K4  fused lift + splat forward.  bev[cell, c] = sum over the cell's points of
- *     depth[pixel, d] * feat[pixel, c]; the frustum tensor never exists.
+ *     depth[point] * feat[pixel(point), c]; the frustum tensor never exists.
  *     Replaces src/modules.py:84 + src/model_baseline.py:79-80,89,102-124 +
- *     src/tools.py:194-208.  Inputs are the staged d_depth_t / d_feat_t and a plan.
+ *     src/tools.py:194-208.  d_depth (BN, D*fH*fW) with batch stride (elements)
+ *     and dtype, d_feat_t from lss_feat_stage, and a plan.
  * K5  fused backward.  d_ddepth (BN,D,fH,fW) = sum_c g*feat, d_dfeat
  *     (BN,C,fH,fW) = sum_d g*depth with g = dbev[cell(point), :] (an exact
  *     gather, as QuickCumsum.backward is); points that were dropped contribute 0.
+ *     The outputs have batch strides (the two gradients may be channel slices of
+ *     one tensor shaped like the conv output) and element type out_dtype.  With
+ *     softmax != 0, d_depth holds the probabilities lss_depth_softmax wrote and
+ *     the first output receives the gradient of the depth LOGITS,
+ *     p * (d_depth - sum_d p * d_depth) (autograd of src/modules.py:77; D <= 128).
+ *     <g, feat> is accumulated in float64.
  * ------------------------------------------------------------------------- */
-int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32_t* d_sorted_points,
-                      const int32_t* d_sorted_cells, const int32_t* d_key_start, const LssGrid* grid,
-                      const LssShape* shape, int32_t layout, float* d_bev, void* stream);
-int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
-                      const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                      int32_t layout, float* d_ddepth, float* d_dfeat, void* stream);
-/* The same with output batch strides (the two gradients may be channel slices of one tensor) and,
- * with softmax != 0, the softmax backward fused: the first output receives the gradient of the depth
- * LOGITS, p * (d_depth - sum_d p * d_depth), p = d_depth_t (autograd of src/modules.py:77; D <= 128).
- * out_dtype (LssDtype) is the element type of both gradient outputs. */
-int lss_liftsplat_bwd_ex(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
-                         const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                         int32_t layout, int32_t softmax, int32_t out_dtype, void* d_ddepth_or_dlogits,
-                         int64_t ddepth_batch_stride, void* d_dfeat, int64_t dfeat_batch_stride,
-                         void* stream);
+int lss_liftsplat_fwd(const void* d_depth, int64_t depth_batch_stride, int32_t depth_dtype,
+                      const float* d_feat_t, const int32_t* d_sorted_rec, const int32_t* d_key_start,
+                      const LssGrid* grid, const LssShape* shape, float* d_bev, void* stream);
+int lss_liftsplat_bwd(const float* d_dbev, const void* d_depth, int64_t depth_batch_stride, int32_t depth_dtype,
+                      const float* d_feat_t, const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
+                      int32_t softmax, int32_t out_dtype, void* d_ddepth_or_dlogits, int64_t ddepth_batch_stride,
+                      void* d_dfeat, int64_t dfeat_batch_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,11 +11,10 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "liblss_b200.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+# LSS_B200_LIB: load another build of the same ABI (kernel-variant experiments, tools/)
+LIB_PATH = os.environ.get("LSS_B200_LIB") or os.path.join(_HERE, LIB_NAME)
 
-ABI_VERSION = 2
-LSS_BEV_NHWC = 0
-LSS_BEV_NCHW = 1
+ABI_VERSION = 3
 LSS_F32, LSS_F16, LSS_BF16 = 0, 1, 2
 
 
@@ -52,19 +51,19 @@ SIGNATURES = {
     "lss_sort_workspace_bytes": (_sz, [_i64, _i32]),
     "lss_sort_ranks": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
     "lss_intervals": (C.c_int, [_p, _i64, _G, _i32, _p, _p, _p, _p, _p]),
-    "lss_pool_dense_fwd": (C.c_int, [_p, _p, _p, _p, _G, _i32, _i32, _i64, _i32, _p, _p]),
-    "lss_pool_dense_bwd": (C.c_int, [_p, _p, _G, _i32, _i32, _i64, _i32, _p, _p]),
-    "lss_lift_stage": (C.c_int, [_p, _p, _S, _p, _p, _p]),
-    "lss_lift_stage_ex": (C.c_int, [_p, _i64, _p, _i64, _S, _i32, _i32, _p, _p, _p]),
-    "lss_liftsplat_fwd": (C.c_int, [_p, _p, _p, _p, _p, _G, _S, _i32, _p, _p]),
-    "lss_liftsplat_bwd": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _p, _p, _p]),
-    "lss_liftsplat_bwd_ex": (C.c_int, [_p, _p, _p, _p, _G, _S, _i32, _i32, _i32, _p, _i64, _p, _i64, _p]),
+    "lss_pool_dense_fwd": (C.c_int, [_p, _p, _p, _G, _i32, _i32, _i64, _p, _p]),
+    "lss_pool_dense_bwd": (C.c_int, [_p, _p, _G, _i32, _i32, _i64, _p, _p]),
+    "lss_feat_stage": (C.c_int, [_p, _i64, _S, _i32, _p, _p]),
+    "lss_depth_softmax": (C.c_int, [_p, _i64, _S, _i32, _p, _p]),
+    "lss_liftsplat_fwd": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _G, _S, _p, _p]),
+    "lss_liftsplat_bwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _G, _S, _i32, _i32, _p, _i64, _p, _i64, _p]),
     "lss_plan_workspace_bytes": (_sz, [_S, _G]),
+    "lss_plan_workspace_control_bytes": (_sz, [_S, _G]),
     "lss_plan_key_count": (_i64, [_G, _i32]),
     "lss_plan_key_tile": (C.c_int, []),
-    "lss_build_plan": (C.c_int, [_p] * 8 + [_G, _S, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "lss_build_plan": (C.c_int, [_p] * 8 + [_G, _S, _p, _p, _p, _p, _p, _sz, _p]),
     "lss_plan_from_geom_workspace_bytes": (_sz, [_i64, _G, _i32]),
-    "lss_build_plan_from_geom": (C.c_int, [_p, _G, _i32, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "lss_build_plan_from_geom": (C.c_int, [_p, _G, _i32, _i64, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lock = threading.Lock()

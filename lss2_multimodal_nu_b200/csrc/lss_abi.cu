@@ -1,6 +1,4 @@
 // extern "C" entry points declared in include/lss_b200.h.
-#include <stdlib.h>
-
 #include "lss_common.cuh"
 #include "lss_geometry.cuh"
 #include "lss_pool.cuh"
@@ -47,13 +45,12 @@ static int launch_geometry(const GeomArgs& ga, const GridDev& g, const LssShape*
 
 static int launch_intervals(const int32_t* sorted_ranks, long long P, const GridDev& g,
                             uint8_t* last_mask, int32_t* sorted_cells, int32_t* cell_range, int32_t* counts,
-                            uint32_t* wipe, long long wipe_words, cudaStream_t st) {
+                            cudaStream_t st) {
   IntervalArgs a;
   a.sorted_ranks = sorted_ranks; a.P = P; a.g = g;
   a.div_b = FastDiv(g.B); a.div_z = FastDiv(g.nx[2]); a.div_y = FastDiv(g.nx[1]);
   a.last_mask = last_mask; a.sorted_cells = sorted_cells;
   a.cell_range = reinterpret_cast<int2*>(cell_range); a.counts = counts;
-  a.wipe = wipe; a.wipe_words = wipe_words;
   long long blocks = (P + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
@@ -63,27 +60,29 @@ static int launch_intervals(const int32_t* sorted_ranks, long long P, const Grid
   return LSS_OK;
 }
 
-// ---- the plan: P1 cells -> P2 scan -> P3 scatter -> P4 order (lss_plan.cuh) ---------------
+// ---- the plan: P1 cells -> P2 scan -> P3 scatter + order (lss_plan.cuh) ---------------
 static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& g, long long P,
-                    long long points_per_sample, int32_t* d_cells, int32_t* d_cell_start,
-                    int32_t* d_sorted_points, int32_t* d_sorted_cells, int32_t* d_counts, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
+                    long long points_per_sample, int32_t* d_cells, int32_t* d_key_start,
+                    int32_t* d_sorted_rec, int32_t* d_counts, void* ws, size_t ws_bytes, cudaStream_t st) {
   KeyMap km;
   int rck = make_keymap(g, &km);
   if (rck) return rck;
   const PlanWorkspace pw = make_plan_workspace(P, km.n_keys);
   LSS_REQUIRE(ws_bytes >= pw.total_bytes, LSS_ERR_WORKSPACE_TOO_SMALL);
-  LSS_REQUIRE(aligned16(ws) && aligned16(d_cell_start), LSS_ERR_MISALIGNED);
+  LSS_REQUIRE(aligned16(ws) && aligned16(d_key_start) && aligned16(d_sorted_rec), LSS_ERR_MISALIGNED);
   char* w = static_cast<char*>(ws);
   uint32_t* cnt = reinterpret_cast<uint32_t*>(w + pw.off_cnt);
-  uint32_t* state = reinterpret_cast<uint32_t*>(w + pw.off_state);
+  uint32_t* done = reinterpret_cast<uint32_t*>(w + pw.off_done);
+  uint32_t* tsum = reinterpret_cast<uint32_t*>(w + pw.off_tsum);
   uint32_t* ctl = reinterpret_cast<uint32_t*>(w + pw.off_ctl);
-  int32_t* tmp_pt = reinterpret_cast<int32_t*>(w + pw.off_tmp_pt);
+  int32_t* keys = reinterpret_cast<int32_t*>(w + pw.off_keys);
+  int32_t* tmp = reinterpret_cast<int32_t*>(w + pw.off_tmp);
   int32_t* long_list = reinterpret_cast<int32_t*>(w + pw.off_long);
 
   PlanCellsArgs ca;
   memset(&ca, 0, sizeof(ca));
-  ca.grid = g; ca.keys = km; ca.P = P; ca.cells = d_cells; ca.cnt = cnt; ca.counts = d_counts; ca.ctl = ctl;
+  ca.grid = g; ca.keys = km; ca.P = P; ca.cells = d_cells; ca.key_of_point = keys; ca.cnt = cnt; ca.tsum = tsum;
+  ca.tile_shift = pw.tile_shift; ca.counts = d_counts; ca.ctl = ctl;
   const unsigned tiles = (unsigned)((P + kPlanTile - 1) / kPlanTile);
   if (ga) {
     ca.geom = *ga;
@@ -100,42 +99,79 @@ static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& 
   LSS_LAUNCH_CHECK("plan_cells_kernel");
 
   PlanScanArgs sa;
-  sa.cnt = cnt; sa.n = km.n_keys; sa.tiles = pw.scan_tiles; sa.cell_start = d_cell_start;
-  sa.state = state; sa.ctl = ctl; sa.counts = d_counts; sa.long_list = long_list;
+  sa.cnt = cnt; sa.tsum = tsum; sa.n = km.n_keys; sa.tiles = pw.scan_tiles; sa.tile_shift = pw.tile_shift;
+  sa.key_start = d_key_start; sa.counts = d_counts;
   plan_scan_kernel<<<(unsigned)pw.scan_tiles, kPlanThreads, 0, st>>>(sa);
   LSS_LAUNCH_CHECK("plan_scan_kernel");
 
   PlanScatterArgs sc;
-  sc.cells = d_cells; sc.P = P; sc.keys = km; sc.cnt = cnt; sc.cell_start = d_cell_start;
-  sc.tmp_pt = tmp_pt; sc.sorted_cells = d_sorted_cells; sc.state = state; sc.scan_tiles = pw.scan_tiles; sc.ctl = ctl;
-  long long blocks = (P + kPlanThreads - 1) / kPlanThreads;
-  const long long cap = (long long)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
+  sc.key_of_point = keys; sc.cells = d_cells; sc.P = P; sc.cnt = cnt; sc.done = done; sc.key_start = d_key_start;
+  sc.n_keys = km.n_keys; sc.tmp = tmp; sc.rec = reinterpret_cast<int2*>(d_sorted_rec); sc.tsum = tsum;
+  sc.scan_tiles = pw.scan_tiles; sc.ctl = ctl; sc.long_list = long_list; sc.keys = km;
+  const long long blocks = (P + kPlanThreads - 1) / kPlanThreads;
   plan_scatter_kernel<<<(unsigned)blocks, kPlanThreads, 0, st>>>(sc);
   LSS_LAUNCH_CHECK("plan_scatter_kernel");
-
-  PlanOrderArgs oa;
-  oa.tmp_pt = tmp_pt; oa.sorted_cells = d_sorted_cells; oa.cell_start = d_cell_start; oa.keys = km; oa.n_cells = km.n_keys;
-  oa.P = P; oa.sorted_points = d_sorted_points; oa.ctl = ctl; oa.long_list = long_list;
-  plan_order_kernel<<<(unsigned)blocks, kPlanThreads, 0, st>>>(oa);
-  LSS_LAUNCH_CHECK("plan_order_kernel");
   return LSS_OK;
 }
 
-template <int kLanes>
-static int launch_bwd(const PoolBwdArgs& a, int blocks, cudaStream_t st) {
-  if (a.softmax || a.out_dtype != LSS_F32) liftsplat_bwd_nhwc_kernel<kLanes, true><<<blocks, kBwdThreads, 0, st>>>(a);
-  else liftsplat_bwd_nhwc_kernel<kLanes, false><<<blocks, kBwdThreads, 0, st>>>(a);
-  LSS_LAUNCH_CHECK("liftsplat_bwd_nhwc_kernel");
-  return LSS_OK;
+// ---- lane layouts of the pooling kernels -----------------------------------------------------
+// a feature row of C floats = L lanes x (kNP float4 [+ one float2]); see lss_pool.cuh
+struct LaneLayout { int L, np, t2, nact; };
+static LaneLayout lane_layout(int C, int min_L) {
+  LaneLayout l;
+  if (C % 32 == 0 && C / 32 <= 4) { l.L = 8; l.np = C / 32; l.t2 = 0; l.nact = 8; return l; }
+  if (C % 32 == 16 && C >= 48 && C <= 112) { l.L = 8; l.np = (C - 16) / 32; l.t2 = 1; l.nact = 8; return l; }
+  int L = 1;
+  while (L * 4 < C) L <<= 1;
+  if (L < min_L) L = min_L;
+  l.L = L; l.np = 1; l.t2 = 0; l.nact = C / 4;
+  return l;
 }
+
 template <bool kFused>
-static int launch_pool_fwd(const PoolFwdArgs& a, int blocks, cudaStream_t st) {
-  if (a.C <= 32) pool_fwd_nhwc_kernel<kFused, 1><<<blocks, kPoolThreads, 0, st>>>(a);
-  else if (a.C <= 64 && a.C % 2 == 0) pool_fwd_nhwc_kernel<kFused, 2><<<blocks, kPoolThreads, 0, st>>>(a);
-  else pool_fwd_nhwc_kernel<kFused, 4><<<blocks, kPoolThreads, 0, st>>>(a);
-  LSS_LAUNCH_CHECK("pool_fwd_nhwc_kernel");
-  return LSS_OK;
+static int launch_pool_fwd(const PoolFwdArgs& a0, int blocks, cudaStream_t st) {
+  PoolFwdArgs a = a0;
+  const LaneLayout l = lane_layout(a.C, 1);
+  a.nact = l.nact;
+#define LSS_FWD_CASE(LL, NP, T2)                                                                  \
+  if (l.L == LL && l.np == NP && l.t2 == T2) {                                                     \
+    pool_fwd_kernel<kFused, LL, NP, (T2 != 0), LSS_FWD_M><<<blocks, kPoolThreads, 0, st>>>(a);     \
+    LSS_LAUNCH_CHECK("pool_fwd_kernel");                                                           \
+    return LSS_OK;                                                                                 \
+  }
+  LSS_FWD_CASE(8, 1, 0) LSS_FWD_CASE(8, 2, 0) LSS_FWD_CASE(8, 3, 0) LSS_FWD_CASE(8, 4, 0)
+  LSS_FWD_CASE(8, 1, 1) LSS_FWD_CASE(8, 2, 1) LSS_FWD_CASE(8, 3, 1)
+  LSS_FWD_CASE(1, 1, 0) LSS_FWD_CASE(2, 1, 0) LSS_FWD_CASE(4, 1, 0) LSS_FWD_CASE(16, 1, 0) LSS_FWD_CASE(32, 1, 0)
+#undef LSS_FWD_CASE
+  return LSS_ERR_UNSUPPORTED;
+}
+
+static int launch_bwd(const PoolBwdArgs& a0, cudaStream_t st) {
+  PoolBwdArgs a = a0;
+  const LaneLayout l = lane_layout(a.C, 8);
+  a.nact = l.nact;
+  const int G = 32 / l.L;
+  int rgw = 1;
+  while (rgw < 8 && rgw * G < a.fH) rgw <<= 1;
+  a.rg_warps = rgw;
+  const int slices = kBwdWarps / rgw;
+  a.d_per_slice = (a.D + slices - 1) / slices;
+  a.row_blocks = (a.fH + rgw * G - 1) / (rgw * G);
+  const long long blocks = (long long)a.BN * a.fW * a.row_blocks;
+  LSS_REQUIRE(blocks < (1ll << 31), LSS_ERR_BAD_DIMENSION);
+  const bool general = a.softmax || a.out_dtype != LSS_F32;
+#define LSS_BWD_CASE(LL, NP, T2)                                                                  \
+  if (l.L == LL && l.np == NP && l.t2 == T2) {                                                     \
+    if (general) liftsplat_bwd_kernel<LL, NP, (T2 != 0), true><<<(unsigned)blocks, kBwdThreads, 0, st>>>(a);  \
+    else liftsplat_bwd_kernel<LL, NP, (T2 != 0), false><<<(unsigned)blocks, kBwdThreads, 0, st>>>(a);         \
+    LSS_LAUNCH_CHECK("liftsplat_bwd_kernel");                                                      \
+    return LSS_OK;                                                                                 \
+  }
+  LSS_BWD_CASE(8, 1, 0) LSS_BWD_CASE(8, 2, 0) LSS_BWD_CASE(8, 3, 0) LSS_BWD_CASE(8, 4, 0)
+  LSS_BWD_CASE(8, 1, 1) LSS_BWD_CASE(8, 2, 1) LSS_BWD_CASE(8, 3, 1)
+  LSS_BWD_CASE(16, 1, 0) LSS_BWD_CASE(32, 1, 0)
+#undef LSS_BWD_CASE
+  return LSS_ERR_UNSUPPORTED;
 }
 }  // namespace lss
 
@@ -247,65 +283,62 @@ int lss_intervals(const int32_t* d_sorted_ranks, int64_t P, const LssGrid* grid,
   int rc = make_grid(grid, B, &g);
   if (rc) return rc;
   return launch_intervals(d_sorted_ranks, P, g, d_last_mask, d_sorted_cells, d_cell_range, d_counts,
-                          nullptr, 0, as_stream(stream));
+                          as_stream(stream));
 }
 
-static int pool_fwd_common(bool fused, const float* d_depth_t, const float* d_feat_t,
-                           const float* d_x, const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
-                           const int32_t* d_cell_start, const LssGrid* grid, int32_t B, int32_t C,
-                           int32_t D, int32_t HW, long long dhw, long long P, int32_t layout, float* d_bev,
-                           cudaStream_t st) {
-  LSS_REQUIRE(d_sorted_points && d_sorted_cells && d_cell_start && d_bev, LSS_ERR_NULL_POINTER);
+static int fill_cta_count(const KeyMap& km) {
+  // fill CTAs: one per SM, so the zero stream runs in the background for the whole kernel
+  long long fill = sm_count();
+  const long long fill_blocks = ((long long)km.n_keys + 31) / 32;
+  if (fill * kPoolWarps > fill_blocks) fill = (fill_blocks + kPoolWarps - 1) / kPoolWarps;
+  if (fill < 1) fill = 1;
+  return (int)fill;
+}
+
+static int pool_fwd_common(bool fused, const void* d_depth, long long depth_bs, int depth_dtype,
+                           const float* d_feat_t, const float* d_x, const int32_t* d_sorted_rec,
+                           const int32_t* d_key_start, const LssGrid* grid, int32_t B, int32_t C, int32_t HW,
+                           long long dhw, long long P, float* d_bev, cudaStream_t st) {
+  LSS_REQUIRE(d_sorted_rec && d_key_start && d_bev, LSS_ERR_NULL_POINTER);
   GridDev g;
   int rc = make_grid(grid, B, &g);
   if (rc) return rc;
   LSS_REQUIRE(C > 0 && C % 4 == 0, LSS_ERR_MISALIGNED);
   LSS_REQUIRE(C <= 128, LSS_ERR_UNSUPPORTED);
-  LSS_REQUIRE(aligned16(d_bev), LSS_ERR_MISALIGNED);
-  LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
+  LSS_REQUIRE(aligned16(d_bev) && aligned16(d_sorted_rec), LSS_ERR_MISALIGNED);
   LSS_REQUIRE(P > 0 && P < (1ll << 30), LSS_ERR_BAD_DIMENSION);
   PoolFwdArgs a;
   memset(&a, 0, sizeof(a));
-  a.depth_t = d_depth_t; a.feat_t = d_feat_t; a.x = d_x;
-  a.sorted_points = d_sorted_points; a.sorted_cells = d_sorted_cells; a.cell_start = d_cell_start;
+  a.depth = d_depth; a.depth_bs = depth_bs; a.depth_dtype = depth_dtype; a.feat_t = d_feat_t; a.x = d_x;
+  a.rec = reinterpret_cast<const int2*>(d_sorted_rec); a.key_start = d_key_start;
   a.bev = d_bev; a.P = P;
   rc = make_keymap(g, &a.keys);
   if (rc) return rc;
-  a.C = C; a.D = D; a.HW = HW;
+  a.C = C; a.HW = HW;
   a.div_dhw = FastDiv((uint32_t)(dhw > 0 ? dhw : 1)); a.div_hw = FastDiv((uint32_t)(HW > 0 ? HW : 1));
-  a.div_g4 = FastDiv((uint32_t)(C / 4));
-  // fill CTAs: one per SM by default, so the zero stream runs in the background for the whole kernel
-  long long fill = sm_count();
-  const long long fill_blocks = ((long long)a.keys.n_keys + 31) / 32;
-  if (fill * kPoolWarps > fill_blocks) fill = (fill_blocks + kPoolWarps - 1) / kPoolWarps;
-  if (const char* e = getenv("LSS_FILL_CTAS")) fill = atoi(e);   // tuning knob
-  if (fill < 1) fill = 1;
-  a.fill_ctas = (int)fill;
-  const long long reduce = (P + (long long)kPoolChunk * kPoolWarps - 1) / ((long long)kPoolChunk * kPoolWarps);
-  const long long blocks = fill + reduce;
+  a.fill_ctas = fill_cta_count(a.keys);
+  const long long per_cta = (long long)LSS_FWD_M * 32 * kPoolWarps;
+  const long long blocks = a.fill_ctas + (P + per_cta - 1) / per_cta;
   LSS_REQUIRE(blocks < (1ll << 31), LSS_ERR_BAD_DIMENSION);
   return fused ? launch_pool_fwd<true>(a, (int)blocks, st) : launch_pool_fwd<false>(a, (int)blocks, st);
 }
 
-int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_points, const int32_t* d_sorted_cells,
-                       const int32_t* d_cell_start, const LssGrid* grid, int32_t B, int32_t C, int64_t P,
-                       int32_t layout, float* d_bev, void* stream) {
+int lss_pool_dense_fwd(const float* d_x, const int32_t* d_sorted_rec, const int32_t* d_key_start,
+                       const LssGrid* grid, int32_t B, int32_t C, int64_t P, float* d_bev, void* stream) {
   LSS_REQUIRE(d_x, LSS_ERR_NULL_POINTER);
   LSS_REQUIRE(aligned16(d_x), LSS_ERR_MISALIGNED);
-  LSS_REQUIRE((long long)P * (C / 4) < (1ll << 32), LSS_ERR_BAD_DIMENSION);   // 16-byte row offsets in 32 bits
-  return pool_fwd_common(false, nullptr, nullptr, d_x, d_sorted_points, d_sorted_cells, d_cell_start, grid, B,
-                         C, 1, 1, 1, P, layout, d_bev, as_stream(stream));
+  LSS_REQUIRE(C > 0 && (long long)P * (C / 4) < (1ll << 31), LSS_ERR_BAD_DIMENSION);   // 16-byte row offsets in 31 bits
+  return pool_fwd_common(false, nullptr, 0, LSS_F32, nullptr, d_x, d_sorted_rec, d_key_start, grid, B, C, 1, 1, P,
+                         d_bev, as_stream(stream));
 }
 
 int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGrid* grid,
-                       int32_t B, int32_t C, int64_t P, int32_t layout, float* d_dx,
-                       void* stream) {
+                       int32_t B, int32_t C, int64_t P, float* d_dx, void* stream) {
   LSS_REQUIRE(d_dbev && d_cells && d_dx, LSS_ERR_NULL_POINTER);
   GridDev g;
   int rc = make_grid(grid, B, &g);
   if (rc) return rc;
   LSS_REQUIRE(C > 0 && C % 4 == 0 && aligned16(d_dbev) && aligned16(d_dx), LSS_ERR_MISALIGNED);
-  LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
   const int G = C / 4;
   const long long n = (long long)P * G;
   LSS_REQUIRE(P > 0 && n < (1ll << 31), LSS_ERR_BAD_DIMENSION);
@@ -319,111 +352,80 @@ int lss_pool_dense_bwd(const float* d_dbev, const int32_t* d_cells, const LssGri
   return LSS_OK;
 }
 
-static int lift_stage_common(const void* d_depth, long long depth_bs, const void* d_feat, long long feat_bs,
-                             const LssShape* shape, int softmax, int dtype, float* d_depth_t, float* d_feat_t,
-                             cudaStream_t st) {
-  LSS_REQUIRE(d_depth && d_feat && d_depth_t && d_feat_t, LSS_ERR_NULL_POINTER);
+int lss_feat_stage(const void* d_feat, int64_t feat_batch_stride, const LssShape* shape, int32_t dtype,
+                   float* d_feat_t, void* stream) {
+  LSS_REQUIRE(d_feat && d_feat_t, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(valid_dtype(dtype), LSS_ERR_UNSUPPORTED);
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  const int HW = shape->fH * shape->fW, BN = shape->B * shape->N, C = shape->C;
+  LSS_REQUIRE(C % 4 == 0 && aligned16(d_feat_t), LSS_ERR_MISALIGNED);
+  LSS_REQUIRE(BN <= 65535, LSS_ERR_BAD_DIMENSION);
+  LSS_REQUIRE(feat_batch_stride >= (long long)C * HW, LSS_ERR_BAD_DIMENSION);
+  const int vec_ok = (dtype == LSS_F32 && HW % 4 == 0 && feat_batch_stride % 4 == 0 && aligned16(d_feat)) ? 1 : 0;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, BN);
+  feat_stage_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_feat, feat_batch_stride, dtype, vec_ok, C, HW, d_feat_t);
+  LSS_LAUNCH_CHECK("feat_stage_kernel");
+  return LSS_OK;
+}
+
+int lss_depth_softmax(const void* d_logits, int64_t logits_batch_stride, const LssShape* shape, int32_t dtype,
+                      float* d_depth, void* stream) {
+  LSS_REQUIRE(d_logits && d_depth, LSS_ERR_NULL_POINTER);
   LSS_REQUIRE(valid_dtype(dtype), LSS_ERR_UNSUPPORTED);
   int rc = check_shape(shape);
   if (rc) return rc;
   const int HW = shape->fH * shape->fW, BN = shape->B * shape->N;
-  const int R = shape->D > shape->C ? shape->D : shape->C;
-  LSS_REQUIRE(BN * 2 <= 65535, LSS_ERR_BAD_DIMENSION);
-  LSS_REQUIRE(depth_bs >= (long long)shape->D * HW && feat_bs >= (long long)shape->C * HW, LSS_ERR_BAD_DIMENSION);
-  dim3 grid((HW + 31) / 32, (R + 31) / 32, BN * 2);
-  if (softmax) {
-    LSS_REQUIRE(shape->D <= kSoftmaxMaxD, LSS_ERR_UNSUPPORTED);
-    lift_stage_softmax_kernel<<<dim3((HW + 31) / 32, BN), 256, 0, st>>>(d_depth, depth_bs, dtype, shape->D, HW,
-                                                                        d_depth_t);
-    LSS_LAUNCH_CHECK("lift_stage_softmax_kernel");
-    lift_stage_kernel<<<grid, 256, 0, st>>>(nullptr, 0, d_feat, feat_bs, dtype, shape->D, shape->C, HW, d_depth_t,
-                                            d_feat_t);
-  } else {
-    lift_stage_kernel<<<grid, 256, 0, st>>>(d_depth, depth_bs, d_feat, feat_bs, dtype, shape->D, shape->C, HW,
-                                            d_depth_t, d_feat_t);
-  }
-  LSS_LAUNCH_CHECK("lift_stage_kernel");
+  LSS_REQUIRE(logits_batch_stride >= (long long)shape->D * HW, LSS_ERR_BAD_DIMENSION);
+  LSS_REQUIRE((long long)BN * HW < (1ll << 31), LSS_ERR_BAD_DIMENSION);
+  const int n = BN * HW;
+  depth_softmax_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(d_logits, logits_batch_stride, dtype,
+                                                                       shape->D, HW, BN, d_depth);
+  LSS_LAUNCH_CHECK("depth_softmax_kernel");
   return LSS_OK;
 }
 
-int lss_lift_stage(const float* d_depth, const float* d_feat, const LssShape* shape,
-                   float* d_depth_t, float* d_feat_t, void* stream) {
-  if (check_shape(shape) != LSS_OK) return check_shape(shape);
-  const long long HW = (long long)shape->fH * shape->fW;
-  return lift_stage_common(d_depth, shape->D * HW, d_feat, shape->C * HW, shape, 0, LSS_F32, d_depth_t, d_feat_t,
-                           as_stream(stream));
-}
-
-int lss_lift_stage_ex(const void* d_depth_or_logits, int64_t depth_batch_stride, const void* d_feat,
-                      int64_t feat_batch_stride, const LssShape* shape, int32_t softmax, int32_t dtype,
-                      float* d_depth_t, float* d_feat_t, void* stream) {
-  return lift_stage_common(d_depth_or_logits, depth_batch_stride, d_feat, feat_batch_stride, shape, softmax ? 1 : 0,
-                           dtype, d_depth_t, d_feat_t, as_stream(stream));
-}
-
-int lss_liftsplat_fwd(const float* d_depth_t, const float* d_feat_t, const int32_t* d_sorted_points,
-                      const int32_t* d_sorted_cells, const int32_t* d_cell_start, const LssGrid* grid,
-                      const LssShape* shape, int32_t layout, float* d_bev, void* stream) {
-  LSS_REQUIRE(d_depth_t && d_feat_t, LSS_ERR_NULL_POINTER);
+int lss_liftsplat_fwd(const void* d_depth, int64_t depth_batch_stride, int32_t depth_dtype,
+                      const float* d_feat_t, const int32_t* d_sorted_rec, const int32_t* d_key_start,
+                      const LssGrid* grid, const LssShape* shape, float* d_bev, void* stream) {
+  LSS_REQUIRE(d_depth && d_feat_t, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(valid_dtype(depth_dtype), LSS_ERR_UNSUPPORTED);
   int rc = check_shape(shape);
   if (rc) return rc;
   LSS_REQUIRE(aligned16(d_feat_t), LSS_ERR_MISALIGNED);
   const int HW = shape->fH * shape->fW;
-  return pool_fwd_common(true, d_depth_t, d_feat_t, nullptr, d_sorted_points, d_sorted_cells, d_cell_start,
-                         grid, shape->B, shape->C, shape->D, HW, (long long)shape->D * HW, shape_points(shape),
-                         layout, d_bev, as_stream(stream));
+  LSS_REQUIRE(depth_batch_stride >= (long long)shape->D * HW, LSS_ERR_BAD_DIMENSION);
+  LSS_REQUIRE((long long)shape->B * shape->N * HW * (shape->C / 4) < (1ll << 31), LSS_ERR_BAD_DIMENSION);
+  return pool_fwd_common(true, d_depth, depth_batch_stride, depth_dtype, d_feat_t, nullptr, d_sorted_rec,
+                         d_key_start, grid, shape->B, shape->C, HW, (long long)shape->D * HW, shape_points(shape),
+                         d_bev, as_stream(stream));
 }
 
-static int liftsplat_bwd_common(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
-                                const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                                int32_t layout, int softmax, int out_dtype, void* d_ddepth, long long ddepth_bs,
-                                void* d_dfeat, long long dfeat_bs, cudaStream_t st) {
-  LSS_REQUIRE(d_dbev && d_depth_t && d_feat_t && d_cells && d_ddepth && d_dfeat, LSS_ERR_NULL_POINTER);
-  LSS_REQUIRE(valid_dtype(out_dtype), LSS_ERR_UNSUPPORTED);
+int lss_liftsplat_bwd(const float* d_dbev, const void* d_depth, int64_t depth_batch_stride, int32_t depth_dtype,
+                      const float* d_feat_t, const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
+                      int32_t softmax, int32_t out_dtype, void* d_ddepth_or_dlogits, int64_t ddepth_batch_stride,
+                      void* d_dfeat, int64_t dfeat_batch_stride, void* stream) {
+  LSS_REQUIRE(d_dbev && d_depth && d_feat_t && d_cells && d_ddepth_or_dlogits && d_dfeat, LSS_ERR_NULL_POINTER);
+  LSS_REQUIRE(valid_dtype(out_dtype) && valid_dtype(depth_dtype), LSS_ERR_UNSUPPORTED);
   int rc = check_shape(shape);
   if (rc) return rc;
   GridDev g;
   rc = make_grid(grid, shape->B, &g);
   if (rc) return rc;
   LSS_REQUIRE(shape->C % 4 == 0 && aligned16(d_dbev) && aligned16(d_feat_t), LSS_ERR_MISALIGNED);
-  LSS_REQUIRE(layout == LSS_BEV_NHWC, LSS_ERR_UNSUPPORTED);
+  LSS_REQUIRE(shape->C <= 128, LSS_ERR_UNSUPPORTED);
   const long long HW = (long long)shape->fH * shape->fW;
-  LSS_REQUIRE(ddepth_bs >= shape->D * HW && dfeat_bs >= shape->C * HW, LSS_ERR_BAD_DIMENSION);
-  LSS_REQUIRE(!softmax || shape->D <= kBwdChunk, LSS_ERR_UNSUPPORTED);
+  LSS_REQUIRE(ddepth_batch_stride >= shape->D * HW && dfeat_batch_stride >= shape->C * HW &&
+                  depth_batch_stride >= shape->D * HW, LSS_ERR_BAD_DIMENSION);
+  LSS_REQUIRE(!softmax || (shape->D <= kBwdMaxD && depth_dtype == LSS_F32), LSS_ERR_UNSUPPORTED);
   PoolBwdArgs a;
-  a.dbev = reinterpret_cast<const float4*>(d_dbev); a.depth_t = d_depth_t;
-  a.feat_t = reinterpret_cast<const float4*>(d_feat_t); a.cells = d_cells;
-  a.ddepth = d_ddepth; a.dfeat = d_dfeat; a.ddepth_bs = ddepth_bs; a.dfeat_bs = dfeat_bs; a.softmax = softmax; a.out_dtype = out_dtype;
-  a.D = shape->D; a.fH = shape->fH; a.fW = shape->fW; a.C = shape->C; a.G = shape->C / 4;
-  a.n_pix = shape->B * shape->N * shape->fH * shape->fW;
-  a.div_fh = FastDiv((uint32_t)shape->fH); a.div_fw = FastDiv((uint32_t)shape->fW);
-  LSS_REQUIRE((long long)g.n_cells * a.G < (1ll << 31), LSS_ERR_BAD_DIMENSION);
-  const int G = a.G;
-  const int blocks = (a.n_pix + kBwdWarps - 1) / kBwdWarps;
-  if (G <= 4) return launch_bwd<4>(a, blocks, st);
-  if (G <= 8) return launch_bwd<8>(a, blocks, st);
-  if (G <= 16) return launch_bwd<16>(a, blocks, st);
-  if (G <= 32) return launch_bwd<32>(a, blocks, st);
-  return LSS_ERR_UNSUPPORTED;
-}
-
-int lss_liftsplat_bwd(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
-                      const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                      int32_t layout, float* d_ddepth, float* d_dfeat, void* stream) {
-  if (check_shape(shape) != LSS_OK) return check_shape(shape);
-  const long long HW = (long long)shape->fH * shape->fW;
-  return liftsplat_bwd_common(d_dbev, d_depth_t, d_feat_t, d_cells, grid, shape, layout, 0, LSS_F32, d_ddepth,
-                              shape->D * HW, d_dfeat, shape->C * HW, as_stream(stream));
-}
-
-int lss_liftsplat_bwd_ex(const float* d_dbev, const float* d_depth_t, const float* d_feat_t,
-                         const int32_t* d_cells, const LssGrid* grid, const LssShape* shape,
-                         int32_t layout, int32_t softmax, int32_t out_dtype, void* d_ddepth_or_dlogits,
-                         int64_t ddepth_batch_stride, void* d_dfeat, int64_t dfeat_batch_stride,
-                         void* stream) {
-  return liftsplat_bwd_common(d_dbev, d_depth_t, d_feat_t, d_cells, grid, shape, layout, softmax ? 1 : 0,
-                              out_dtype, d_ddepth_or_dlogits, ddepth_batch_stride, d_dfeat, dfeat_batch_stride,
-                              as_stream(stream));
+  memset(&a, 0, sizeof(a));
+  a.dbev = d_dbev; a.depth = d_depth; a.depth_bs = depth_batch_stride; a.depth_dtype = depth_dtype;
+  a.feat_t = d_feat_t; a.cells = d_cells;
+  a.ddepth = d_ddepth_or_dlogits; a.dfeat = d_dfeat; a.ddepth_bs = ddepth_batch_stride; a.dfeat_bs = dfeat_batch_stride;
+  a.softmax = softmax ? 1 : 0; a.out_dtype = out_dtype;
+  a.D = shape->D; a.fH = shape->fH; a.fW = shape->fW; a.C = shape->C; a.BN = shape->B * shape->N;
+  return launch_bwd(a, as_stream(stream));
 }
 
 size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid) {
@@ -433,6 +435,15 @@ size_t lss_plan_workspace_bytes(const LssShape* shape, const LssGrid* grid) {
   KeyMap km;
   if (make_keymap(g, &km) != LSS_OK) return 0;
   return make_plan_workspace(shape_points(shape), km.n_keys).total_bytes;
+}
+
+size_t lss_plan_workspace_control_bytes(const LssShape* shape, const LssGrid* grid) {
+  if (check_shape(shape) != LSS_OK) return 0;
+  GridDev g;
+  if (make_grid(grid, shape->B, &g) != LSS_OK) return 0;
+  KeyMap km;
+  if (make_keymap(g, &km) != LSS_OK) return 0;
+  return make_plan_workspace(shape_points(shape), km.n_keys).control_bytes;
 }
 
 int64_t lss_plan_key_count(const LssGrid* grid, int32_t B) {
@@ -447,11 +458,10 @@ int lss_plan_key_tile(void) { return kKeyTile; }
 int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, const float* d_rots,
                    const float* d_trans, const float* d_intrins, const float* d_post_rots,
                    const float* d_post_trans, const LssGrid* grid, const LssShape* shape,
-                   int32_t* d_cells, int32_t* d_cell_start, int32_t* d_sorted_points,
-                   int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace, size_t workspace_bytes,
-                   void* stream) {
+                   int32_t* d_cells, int32_t* d_key_start, int32_t* d_sorted_rec, int32_t* d_counts,
+                   void* d_workspace, size_t workspace_bytes, void* stream) {
   LSS_REQUIRE(d_us && d_vs && d_ds && d_rots && d_trans && d_intrins && d_post_rots && d_post_trans &&
-                  d_cells && d_cell_start && d_sorted_points && d_sorted_cells && d_counts && d_workspace,
+                  d_cells && d_key_start && d_sorted_rec && d_counts && d_workspace,
               LSS_ERR_NULL_POINTER);
   int rc = check_shape(shape);
   if (rc) return rc;
@@ -465,22 +475,20 @@ int lss_build_plan(const float* d_us, const float* d_vs, const float* d_ds, cons
   ga.rots = d_rots; ga.intrins = d_intrins; ga.post_rots = d_post_rots;
   ga.raw = 1; ga.N = shape->N; ga.D = shape->D; ga.fH = shape->fH; ga.fW = shape->fW;
   const long long P = shape_points(shape);
-  return run_plan(&ga, nullptr, g, P, P / shape->B, d_cells, d_cell_start, d_sorted_points, d_sorted_cells,
-                  d_counts, d_workspace, workspace_bytes, as_stream(stream));
+  return run_plan(&ga, nullptr, g, P, P / shape->B, d_cells, d_key_start, d_sorted_rec, d_counts, d_workspace,
+                  workspace_bytes, as_stream(stream));
 }
 
 int lss_build_plan_from_geom(const float* d_geom, const LssGrid* grid, int32_t B, int64_t P,
-                             int32_t* d_cells, int32_t* d_cell_start, int32_t* d_sorted_points,
-                             int32_t* d_sorted_cells, int32_t* d_counts, void* d_workspace,
-                             size_t workspace_bytes, void* stream) {
-  LSS_REQUIRE(d_geom && d_cells && d_cell_start && d_sorted_points && d_sorted_cells && d_counts && d_workspace,
-              LSS_ERR_NULL_POINTER);
+                             int32_t* d_cells, int32_t* d_key_start, int32_t* d_sorted_rec, int32_t* d_counts,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+  LSS_REQUIRE(d_geom && d_cells && d_key_start && d_sorted_rec && d_counts && d_workspace, LSS_ERR_NULL_POINTER);
   GridDev g;
   int rc = make_grid(grid, B, &g);
   if (rc) return rc;
   LSS_REQUIRE(P > 0 && P < (1ll << 30) && P % B == 0, LSS_ERR_BAD_DIMENSION);
-  return run_plan(nullptr, d_geom, g, P, P / B, d_cells, d_cell_start, d_sorted_points, d_sorted_cells,
-                  d_counts, d_workspace, workspace_bytes, as_stream(stream));
+  return run_plan(nullptr, d_geom, g, P, P / B, d_cells, d_key_start, d_sorted_rec, d_counts, d_workspace,
+                  workspace_bytes, as_stream(stream));
 }
 
 size_t lss_plan_from_geom_workspace_bytes(int64_t P, const LssGrid* grid, int32_t B) {
@@ -489,11 +497,5 @@ size_t lss_plan_from_geom_workspace_bytes(int64_t P, const LssGrid* grid, int32_
   if (P <= 0 || P >= (1ll << 30) || make_grid(grid, B, &g) != LSS_OK || make_keymap(g, &km) != LSS_OK) return 0;
   return make_plan_workspace(P, km.n_keys).total_bytes;
 }
-
-#ifdef LSS_PHASE_TIMING
-int lss_debug_phase_ts(int kernel, unsigned long long* host_out, int n) {
-  return (int)cudaMemcpyFromSymbol(host_out, g_phase_ts, (size_t)n * 8, (size_t)kernel * 4096 * 16 * 8);
-}
-#endif
 
 }  // extern "C"

@@ -9,8 +9,7 @@ namespace lss {
 // K3: runs of equal ranks in the sorted order.  Replaces the boundary mask of
 // QuickCumsum.forward (reference src/tools.py:196-197): `last` marks the last
 // point of every run.  Heads/tails also record the run's [start, end) in a
-// dense table indexed by OUTPUT cell, which is what lets K4 own every output
-// voxel (zeros included) without a separate fill + scatter.
+// dense table indexed by OUTPUT cell.
 // --------------------------------------------------------------------------
 struct IntervalArgs {
   const int32_t* sorted_ranks;
@@ -21,9 +20,6 @@ struct IntervalArgs {
   int32_t* sorted_cells;  // or null: output cell of every kept sorted point
   int2* cell_range;     // (n_cells) zero on entry
   int32_t* counts;      // {K, V} zero on entry, or null
-  // control words of the sort to wipe for the next call (fused plan path)
-  uint32_t* wipe;
-  long long wipe_words;
 };
 
 __global__ void __launch_bounds__(256)
@@ -33,7 +29,6 @@ intervals_kernel(IntervalArgs a) {
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  for (long long w = first; w < a.wipe_words; w += stride) a.wipe[w] = 0u;
   int kept = 0, tails = 0;
   for (long long i = first; i < a.P; i += stride) {
     const int32_t r = a.sorted_ranks[i];
@@ -77,85 +72,72 @@ intervals_kernel(IntervalArgs a) {
 }
 
 // --------------------------------------------------------------------------
-// Lift staging: (BN, R, HW) -> (BN*HW, R) for R = D (depth) and R = C (context)
-// through a padded 32x32 shared-memory tile; reads and writes are coalesced.
-// grid = (ceil(HW/32), ceil(max(D,C)/32), BN * 2)  [z even: depth, odd: feat]
+// Lift staging.  The pooling kernels want one contiguous row of C context
+// values per pixel: feat (BN, C, HW) -> feat_t (BN*HW, C) through a padded
+// 32x32 shared-memory tile; 128-bit loads along HW where the input allows it,
+// 128-bit stores along C always.  The depth distribution is read in place
+// (it is indexed by POINT id: (BN, D, HW) is the reference's own flattening),
+// unless it has to be computed first (softmax below).
+// grid = (ceil(HW/32), ceil(C/32), BN)
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-lift_stage_kernel(const void* __restrict__ depth, long long depth_bs, const void* __restrict__ feat,
-                  long long feat_bs, int dtype, int D, int C, int HW, float* __restrict__ depth_t,
+feat_stage_kernel(const void* __restrict__ feat, long long feat_bs, int dtype, int vec_ok, int C, int HW,
                   float* __restrict__ feat_t) {
   __shared__ float tile[32][33];
-  const int which = blockIdx.z & 1;
-  const int bn = blockIdx.z >> 1;
-  const int R = which ? C : D;
-  if (!which && depth == nullptr) return;              // depth staged elsewhere (softmax variant)
-  const void* src = which ? feat : depth;
-  const size_t sbase = (size_t)bn * (which ? feat_bs : depth_bs);
-  float* dst = (which ? feat_t : depth_t) + (size_t)bn * HW * R;
-  const int r0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-  if (r0 >= R) return;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int bn = blockIdx.z;
+  const size_t sbase = (size_t)bn * feat_bs;
+  float* dst = feat_t + (size_t)bn * HW * C;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int t = threadIdx.x;
+  if (vec_ok && p0 + 32 <= HW) {                       // float32, 16-byte aligned rows: one float4 per thread
+    const int c = c0 + (t >> 3), q = t & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(feat) + sbase + (size_t)c * HW + p0) + q);
+    float* row = tile[t >> 3];
+    row[4 * q + 0] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+  } else {
+    const int tx = t & 31, ty = t >> 5;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int r = r0 + ty + k * 8, p = p0 + tx;
-    tile[ty + k * 8][tx] = (r < R && p < HW) ? load_as_float(src, sbase + (size_t)r * HW + p, dtype) : 0.0f;
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + k * 8, p = p0 + tx;
+      tile[ty + k * 8][tx] = (c < C && p < HW) ? load_as_float(feat, sbase + (size_t)c * HW + p, dtype) : 0.0f;
+    }
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int p = p0 + ty + k * 8, r = r0 + tx;
-    if (p < HW && r < R) dst[(size_t)p * R + r] = tile[tx][ty + k * 8];
+  // thread -> pixel t>>3, channels 4*(t&7) .. +3 of the tile (C % 4 == 0: a quad is inside or outside)
+  const int p = p0 + (t >> 3), cq = 4 * (t & 7);
+  if (p < HW && c0 + cq < C) {
+    const float4 v = make_float4(tile[cq + 0][t >> 3], tile[cq + 1][t >> 3], tile[cq + 2][t >> 3], tile[cq + 3][t >> 3]);
+    *reinterpret_cast<float4*>(dst + (size_t)p * C + c0 + cq) = v;
   }
 }
 
 // Producer fusion: the depth distribution is softmax over the D logit channels
-// (reference src/modules.py:76-77, `x.softmax(dim=1)`), computed here while staging, so the
-// probabilities are written once, pixel-major, and the (B*N, D, fH, fW) probability tensor of the
-// reference never exists.  One CTA = 32 pixels x all D logits (tile in shared memory):
-// p = exp(x - max) / sum, the expression torch evaluates.
-constexpr int kSoftmaxMaxD = 128;
+// (reference src/modules.py:76-77, `x.softmax(dim=1)`).  One thread per pixel, lanes along HW
+// (coalesced): p = exp(x - max) / sum, the expression torch evaluates, written float32 in the
+// (BN, D, HW) point order the pooling kernels index by point id.
 __global__ void __launch_bounds__(256)
-lift_stage_softmax_kernel(const void* __restrict__ logits, long long logits_bs, int dtype, int D, int HW,
-                          float* __restrict__ depth_t) {
-  __shared__ float tile[kSoftmaxMaxD][33];
-  __shared__ float s_inv[32];
-  const int bn = blockIdx.y, p0 = blockIdx.x * 32;
-  const size_t sbase = (size_t)bn * logits_bs;
-  float* dst = depth_t + (size_t)bn * HW * D;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int r = ty; r < D; r += 8) {
-    const int p = p0 + tx;
-    tile[r][tx] = (p < HW) ? load_as_float(logits, sbase + (size_t)r * HW + p, dtype) : 0.0f;
-  }
-  __syncthreads();
-  if (ty == 0) {                                      // one lane per pixel: max, then the sum of exp
-    float m = tile[0][tx];
-    for (int r = 1; r < D; ++r) m = fmaxf(m, tile[r][tx]);
-    float sum = 0.f;
-    for (int r = 0; r < D; ++r) {
-      const float e = expf(tile[r][tx] - m);
-      tile[r][tx] = e;
-      sum += e;
-    }
-    s_inv[tx] = sum;
-  }
-  __syncthreads();
-  for (int k = ty; k < 32; k += 8) {                  // pixel k of the tile, lanes along d: coalesced rows
-    const int p = p0 + k;
-    if (p >= HW) continue;
-    const float sum = s_inv[k];
-    for (int r = tx; r < D; r += 32) dst[(size_t)p * D + r] = tile[r][k] / sum;
-  }
+depth_softmax_kernel(const void* __restrict__ logits, long long logits_bs, int dtype, int D, int HW, int BN,
+                     float* __restrict__ depth_p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BN * HW) return;
+  const int bn = i / HW, hw = i - bn * HW;
+  const size_t src = (size_t)bn * logits_bs + hw;
+  float* dst = depth_p + (size_t)bn * D * HW + hw;
+  float m = load_as_float(logits, src, dtype);
+  for (int d = 1; d < D; ++d) m = fmaxf(m, load_as_float(logits, src + (size_t)d * HW, dtype));
+  float sum = 0.f;
+  for (int d = 0; d < D; ++d) sum += expf(load_as_float(logits, src + (size_t)d * HW, dtype) - m);
+  for (int d = 0; d < D; ++d) dst[(size_t)d * HW] = expf(load_as_float(logits, src + (size_t)d * HW, dtype) - m) / sum;
 }
 
 // --------------------------------------------------------------------------
 // K4 / K4a forward, channels-innermost BEV.
 //
 // The BEV map is (cell, C) with cell = ((b*X + x)*Y + y)*Z + z, one voxel = one
-// contiguous line, and the plan's point list is sorted by the cell's tile-major
-// key (KeyMap), so key k owns sorted_points[key_start[k] .. key_start[k+1]) and
-// neighbours in the list are neighbours on the map.  Every output element is
+// contiguous line, and the plan's record list {cell, point} is sorted by the
+// cell's tile-major key (KeyMap), so key k owns rec[key_start[k] .. key_start[k+1])
+// and neighbours in the list are neighbours on the map.  Every output element is
 // written exactly once (this is the torch.zeros + index_put + cat of reference
 // src/model_baseline.py:120-124) by two kinds of CTAs that run side by side:
 //   * FILL CTAs (one per SM) stream zeros into the empty voxels (75 % of the map
@@ -165,270 +147,314 @@ lift_stage_softmax_kernel(const void* __restrict__ logits, long long logits_bs, 
 //     the map -- leaves as ONE bulk async store (TMA engine, cp.async.bulk
 //     shared -> global from a 2 KB zero block), so the zero stream costs the SM
 //     neither issue slots nor load/store queue entries;
-//   * REDUCE CTAs do the warp-level segmented reduction over the sorted point
-//     list.  A warp takes 32 consecutive sorted points -- the unit of work is the
-//     POINT, so dense and sparse regions of the map cost the same -- and owns
-//     the intervals that START among them; the last one is followed into the
-//     next chunk.  One coalesced load brings point ids and cells, the lanes
-//     decode them, gather the depths and stage {feature-row offset, depth, cell}
-//     in shared memory; then the warp walks the records in order with
-//     (kS - 1) * kU feature-row gathers in flight (software pipeline), every lane
-//     owning kVec channels (C = 64: 32 lanes x 8 bytes = one 256-byte row per
-//     load), closing the running sum at every interval head.  No cumsum, no
-//     atomics, summation in sort order: bit-reproducible.
-//   kFused:  acc += depth_t[pixel, d] * feat_t[pixel, :]   (K4: the frustum tensor
+//   * REDUCE CTAs do the warp-level segmented reduction over the sorted records.
+//     The unit of work is the POINT (dense and sparse regions of the map cost the
+//     same): a warp takes kM*32 consecutive records.  Its lanes first decode one
+//     record each -- feature-row offset, depth value (read in place, indexed by
+//     point id), interval-head flag -- into shared memory.  Then the warp splits
+//     into G = 32/L WALKERS of L lanes; a walker owns the intervals that START in
+//     its share of the records (the last one is followed into the records after
+//     it) and walks them in order, one 128-bit gather per lane and part of the
+//     feature row (L lanes x kNP x 16 bytes [+ L x 8] = one row), so one warp
+//     instruction gathers / accumulates G points.  A running sum is closed
+//     (stored, zeroed) at every interval head.  No cumsum, no atomics, summation
+//     in sort order: bit-reproducible.
+//   kFused:  acc += depth[point] * feat_t[pixel(point), :]   (K4: the frustum tensor
 //            of src/modules.py:84 is never formed)
-//   !kFused: acc += x[point, :]                             (K4a)
+//   !kFused: acc += x[point, :]                               (K4a)
 // --------------------------------------------------------------------------
 struct PoolFwdArgs {
-  const float* depth_t;           // (BN*HW, D)   fused
+  const void* depth;              // (BN, D*HW) depth distribution, batch stride depth_bs, dtype depth_dtype  [fused]
+  long long depth_bs;
+  int depth_dtype;
   const float* feat_t;            // (BN*HW, C)   fused
   const float* x;                 // (P, C)       dense
-  const int32_t* sorted_points;   // (P) sorted by output cell, ascending point id inside a cell
-  const int32_t* sorted_cells;    // (P) output cell of each sorted point, -1 beyond the K kept points
-  const int32_t* cell_start;      // (n_keys + 1) interval bounds, indexed by key
+  const int2* rec;                // (P) {output cell, point id} by (key, point id); cell -1 beyond the K kept points
+  const int32_t* key_start;       // (n_keys + 1) interval bounds, indexed by key
   float* bev;                     // (n_cells, C)
   long long P;
   KeyMap keys;
   int fill_ctas;                  // CTAs [0, fill_ctas) zero-fill, the rest reduce
-  int C, D, HW;
-  FastDiv div_dhw, div_hw, div_g4;
+  int C, HW;
+  int nact;                       // lanes of a walker that own channels (generic layouts: C/4 <= L)
+  FastDiv div_dhw, div_hw;
 };
 
 constexpr int kPoolThreads = 256;
 constexpr int kPoolWarps = kPoolThreads / 32;
-constexpr int kPoolChunk = 32;    // sorted points per reduce warp
 constexpr int kZeroBytes = 2048;  // zero block in shared memory: source of the bulk zero stores
-constexpr int kPoolRec = 64;      // staged records per warp: the chunk + the tail of its last interval
 
-template <int kVec> struct VecOf;
-template <> struct VecOf<1> { using type = float; };
-template <> struct VecOf<2> { using type = float2; };
-template <> struct VecOf<4> { using type = float4; };
+#ifndef LSS_FWD_MINB
+#define LSS_FWD_MINB 3
+#endif
+#ifndef LSS_FWD_M
+#define LSS_FWD_M 1
+#endif
+#ifndef LSS_BWD_MINB
+#define LSS_BWD_MINB 2
+#endif
 
-template <int kVec> __device__ __forceinline__ void vec_zero(typename VecOf<kVec>::type& v);
-template <> __device__ __forceinline__ void vec_zero<1>(float& v) { v = 0.f; }
-template <> __device__ __forceinline__ void vec_zero<2>(float2& v) { v = make_float2(0.f, 0.f); }
-template <> __device__ __forceinline__ void vec_zero<4>(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
-
-__device__ __forceinline__ void vec_fma(float d, const float& f, float& a) { a = fmaf(d, f, a); }
-__device__ __forceinline__ void vec_fma(float d, const float2& f, float2& a) {
-  a.x = fmaf(d, f.x, a.x); a.y = fmaf(d, f.y, a.y);
-}
-__device__ __forceinline__ void vec_fma(float d, const float4& f, float4& a) {
+__device__ __forceinline__ void f4_fma(float d, const float4& f, float4& a) {
   a.x = fmaf(d, f.x, a.x); a.y = fmaf(d, f.y, a.y); a.z = fmaf(d, f.z, a.z); a.w = fmaf(d, f.w, a.w);
 }
 
-#ifndef LSS_FWD_MINB
-#define LSS_FWD_MINB 4
-#endif
-#ifndef LSS_FWD_STAGES
-#define LSS_FWD_STAGES 4
-#endif
-#ifndef LSS_FWD_STAGES4
-#define LSS_FWD_STAGES4 2
-#endif
-#ifndef LSS_BWD_MINB
-#define LSS_BWD_MINB 4
-#endif
-template <bool kFused, int kVec>
-__global__ void __launch_bounds__(kPoolThreads, LSS_FWD_MINB)
-pool_fwd_nhwc_kernel(PoolFwdArgs a) {
-  using V = typename VecOf<kVec>::type;
-  constexpr int kU = 4;                                      // gathers per pipeline stage
-  constexpr int kS = kVec == 4 ? LSS_FWD_STAGES4 : LSS_FWD_STAGES;   // stages: (kS - 1) * kU gathers in flight
+// zero stream of the forward (see above); returns when the CTA's share of the empty voxels is written
+__device__ __forceinline__ void pool_fill_zeros(const PoolFwdArgs& a, float4* s_zero) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) phase_stamp_any(2, warp * 2);
-
-  // ======================= FILL: zeros into the empty voxels ==========================
-  // A warp takes 32 consecutive KEYS (tile-major order, KeyMap): their interval bounds are one
-  // coalesced load; every group of 8 keys is 8 consecutive voxels of one tile row, i.e. one
-  // contiguous piece of the map, covered with 128-bit stores wherever the voxel is empty.
-  if (static_cast<int>(blockIdx.x) < a.fill_ctas) {
-    // the zeros come from a 2 KB block of shared memory and leave through the TMA engine (bulk
-    // async stores, one instruction per contiguous piece), so they occupy neither the warps' issue
-    // slots nor the load/store queues the REDUCE warps' gathers go through
-    __shared__ __align__(128) float4 s_zero[kZeroBytes / 16];
-    for (int e = threadIdx.x; e < kZeroBytes / 16; e += kPoolThreads) s_zero[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    const uint32_t zsrc = static_cast<uint32_t>(__cvta_generic_to_shared(s_zero));
-    const int n_blocks = (a.keys.n_keys + 31) >> 5;
-    const int stride = a.fill_ctas * kPoolWarps;
-    const uint32_t line_bytes = static_cast<uint32_t>(a.C) * 4u;
-    int blk = blockIdx.x * kPoolWarps + warp;
-    if (blk >= n_blocks) return;
-    auto bounds = [&](int bk, int& lo, int& hi) {
-      const int k = (bk << 5) + lane;
-      lo = 0; hi = 1;                                        // beyond the key space: not ours to write
-      if (k < a.keys.n_keys) { lo = __ldg(a.cell_start + k); hi = __ldg(a.cell_start + k + 1); }
-    };
-    int lo, hi;
-    bounds(blk, lo, hi);
-    while (true) {
-      const int nxt = blk + stride;
-      int nlo = 0, nhi = 1;
-      if (nxt < n_blocks) bounds(nxt, nlo, nhi);             // prefetch before the stores go out
-      const int k = (blk << 5) + lane;
-      const int mycell = (k < a.keys.n_keys) ? a.keys.cell_of_key(static_cast<uint32_t>(k)) : -1;
-      const bool empty = mycell >= 0 && hi == lo;
-      const uint32_t em = __ballot_sync(0xffffffffu, empty);
-      // maximal runs of empty keys inside a group of 8 (= contiguous voxels): the first lane of a
-      // run stores the whole run, at most kZeroBytes at a time
-      if (empty) {
-        const uint32_t g8 = (em >> (lane & 24)) & 0xffu;      // this group's 8 bits
-        const int j = lane & 7;
-        if (j == 0 || !((g8 >> (j - 1)) & 1u)) {              // run head
-          const uint32_t rest = (~(g8 >> j)) & 0xffu;         // first non-empty key after the head
-          const int len = rest ? __ffs(rest) - 1 : 8 - j;
-          char* dst = reinterpret_cast<char*>(a.bev) + (size_t)mycell * line_bytes;
-          uint32_t left = static_cast<uint32_t>(len) * line_bytes;
-          while (left) {
-            const uint32_t n = left < static_cast<uint32_t>(kZeroBytes) ? left : static_cast<uint32_t>(kZeroBytes);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                         :: "l"(dst), "r"(zsrc), "r"(n) : "memory");
-            dst += n; left -= n;
-          }
+  for (int e = threadIdx.x; e < kZeroBytes / 16; e += kPoolThreads) s_zero[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t zsrc = static_cast<uint32_t>(__cvta_generic_to_shared(s_zero));
+  const int n_blocks = (a.keys.n_keys + 31) >> 5;
+  const int stride = a.fill_ctas * kPoolWarps;
+  const uint32_t line_bytes = static_cast<uint32_t>(a.C) * 4u;
+  int blk = blockIdx.x * kPoolWarps + warp;
+  if (blk >= n_blocks) return;
+  auto bounds = [&](int bk, int& lo, int& hi) {
+    const int k = (bk << 5) + lane;
+    lo = 0; hi = 1;                                        // beyond the key space: not ours to write
+    if (k < a.keys.n_keys) { lo = __ldg(a.key_start + k); hi = __ldg(a.key_start + k + 1); }
+  };
+  int lo, hi;
+  bounds(blk, lo, hi);
+  while (true) {
+    const int nxt = blk + stride;
+    int nlo = 0, nhi = 1;
+    if (nxt < n_blocks) bounds(nxt, nlo, nhi);             // prefetch before the stores go out
+    const int k = (blk << 5) + lane;
+    const int mycell = (k < a.keys.n_keys) ? a.keys.cell_of_key(static_cast<uint32_t>(k)) : -1;
+    const bool empty = mycell >= 0 && hi == lo;
+    const uint32_t em = __ballot_sync(0xffffffffu, empty);
+    // maximal runs of empty keys inside a group of 8 (= contiguous voxels): the first lane of a
+    // run stores the whole run, at most kZeroBytes at a time
+    if (empty) {
+      const uint32_t g8 = (em >> (lane & 24)) & 0xffu;      // this group's 8 bits
+      const int j = lane & 7;
+      if (j == 0 || !((g8 >> (j - 1)) & 1u)) {              // run head
+        const uint32_t rest = (~(g8 >> j)) & 0xffu;         // first non-empty key after the head
+        const int len = rest ? __ffs(rest) - 1 : 8 - j;
+        char* dst = reinterpret_cast<char*>(a.bev) + (size_t)mycell * line_bytes;
+        uint32_t left = static_cast<uint32_t>(len) * line_bytes;
+        while (left) {
+          const uint32_t n = left < static_cast<uint32_t>(kZeroBytes) ? left : static_cast<uint32_t>(kZeroBytes);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       :: "l"(dst), "r"(zsrc), "r"(n) : "memory");
+          dst += n; left -= n;
         }
       }
-      if (nxt >= n_blocks) break;
-      blk = nxt; lo = nlo; hi = nhi;
     }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the zero block must outlive the reads
-    if (lane == 0) phase_stamp_any(2, warp * 2 + 1);
+    if (nxt >= n_blocks) break;
+    blk = nxt; lo = nlo; hi = nhi;
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the zero block must outlive the reads
+}
+
+// first set bit at a position >= pos in the kW-word mask h (kW * 32 if none)
+template <int kW>
+__device__ __forceinline__ int first_bit_from(const uint32_t (&h)[kW], int pos) {
+  int res = kW * 32;
+#pragma unroll
+  for (int w = kW - 1; w >= 0; --w) {
+    uint32_t bits = h[w];
+    const int lo = pos - w * 32;
+    if (lo >= 32) bits = 0u;
+    else if (lo > 0) bits &= 0xffffffffu << lo;
+    if (bits) res = w * 32 + __ffs(bits) - 1;
+  }
+  return res;
+}
+
+template <bool kFused, int L, int kNP, bool kT2, int kM>
+__global__ void __launch_bounds__(kPoolThreads, (kNP >= 3 ? 2 : LSS_FWD_MINB))
+pool_fwd_kernel(PoolFwdArgs a) {
+  constexpr int G = 32 / L;             // walkers per warp
+  constexpr int kW = kM + 1;            // staged 32-record words: the chunk + one word of look-ahead
+  constexpr int NR = kW * 32;
+  constexpr int S = kM * 32 / G;        // records per walker (a divisor of 32 or 64)
+  constexpr int U = 4;                  // walk steps whose gathers are issued together
+  static_assert(S >= 1 && (S <= 32 ? 32 % S == 0 : S == 64), "a walker's share must not straddle mask words unevenly");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  __shared__ __align__(128) float4 s_zero[kZeroBytes / 16];
+  if (static_cast<int>(blockIdx.x) < a.fill_ctas) {
+    pool_fill_zeros(a, s_zero);
     return;
   }
 
-  // ======================= REDUCE: segmented sums over the sorted points ==============
-  __shared__ uint4 s_off[kPoolWarps][kPoolRec / 4];          // feature-row offset (16-byte units)
-  __shared__ float4 s_dep[kPoolWarps][kPoolRec / 4];         // depth probability
-  __shared__ int s_cell[kPoolWarps][kPoolChunk];             // output cell (heads only lie in the chunk)
-  const long long i0 = ((long long)(blockIdx.x - a.fill_ctas) * kPoolWarps + warp) * kPoolChunk;
+  // ======================= REDUCE: segmented sums over the sorted records ==============
+  __shared__ uint2 s_rec[kPoolWarps][NR + G];               // {row offset (16-byte units) | head << 31, depth bits}
+  __shared__ int s_cell[kPoolWarps][NR];
+  const long long i0 = ((long long)(blockIdx.x - a.fill_ctas) * kPoolWarps + warp) * (kM * 32);
   if (i0 >= a.P) return;
-  const long long i = i0 + lane;
-  // one round of loads: this chunk's and the next chunk's ids and cells, and the cell before the chunk
-  int cell = -1, ncell = -1, pt = 0, npt = 0;
-  if (i < a.P) cell = __ldg(a.sorted_cells + i);
-  if (i + kPoolChunk < a.P) ncell = __ldg(a.sorted_cells + i + kPoolChunk);
-  int prev = (lane == 0 && i0 > 0) ? __ldg(a.sorted_cells + i0 - 1) : -1;
-  if (i < a.P) pt = __ldg(a.sorted_points + i);
-  if (i + kPoolChunk < a.P) npt = __ldg(a.sorted_points + i + kPoolChunk);
-  {
-    const int up = __shfl_up_sync(0xffffffffu, cell, 1);
-    if (lane > 0) prev = up;
+  // ---- one round of loads: the chunk's and the look-ahead word's records ----
+  int cell[kW], pt[kW];
+#pragma unroll
+  for (int w = 0; w < kW; ++w) {
+    const long long i = i0 + w * 32 + lane;
+    cell[w] = -1; pt[w] = 0;
+    if (i < a.P) { const int2 r = __ldg(a.rec + i); cell[w] = r.x; pt[w] = r.y; }
   }
-  const uint32_t hb = __ballot_sync(0xffffffffu, cell >= 0 && cell != prev);   // interval heads
-  if (hb == 0u) { if (lane == 0) phase_stamp_any(2, warp * 2 + 1); return; }   // an earlier warp owns all of it
-  const uint32_t vb = __ballot_sync(0xffffffffu, cell >= 0);  // kept points are a prefix of the chunk
-  const int nv = __popc(vb);
-  const int h0 = __ffs(hb) - 1;                              // first owned point
-  const int last_cell = __shfl_sync(0xffffffffu, cell, nv - 1);
-  // tail of the last interval inside the next chunk (a prefix of it)
-  const uint32_t cont = __ballot_sync(0xffffffffu, nv == kPoolChunk && ncell == last_cell);
-  const int tail = (cont == 0xffffffffu) ? 32 : __ffs(~cont) - 1;
-  const int n_rec = nv - h0 + tail;                          // records to walk: [h0, nv) + tail
-
-  const uint32_t nact = static_cast<uint32_t>(a.C / kVec);   // lanes that own channels
-  const bool active = lane < nact;                           // idle lanes (C < 32 * kVec) shadow lane 0:
-  const uint32_t vlane = active ? lane : 0u;                 // they gather valid data and never store
-  const char* src = reinterpret_cast<const char*>(reinterpret_cast<const V*>(kFused ? a.feat_t : a.x) + vlane);
-  const uint32_t row16 = static_cast<uint32_t>(a.C) >> 2;    // 16-byte units per feature row
-  auto gather = [&](uint32_t off16) { return __ldg(reinterpret_cast<const V*>(src + ((size_t)off16 << 4))); };
-  V* out = reinterpret_cast<V*>(a.bev) + vlane;
-  uint32_t* offs = reinterpret_cast<uint32_t*>(s_off[warp]);
-  float* deps = reinterpret_cast<float*>(s_dep[warp]);
-
-  // ---- stage the records, shifted so that the first owned point is record 0 ----
-  auto record = [&](int p, uint32_t& off16, float& dv) {
-    if (kFused) {
-      uint32_t bn, rem, d, hw;
-      a.div_dhw.divmod(static_cast<uint32_t>(p), bn, rem);
-      a.div_hw.divmod(rem, d, hw);
-      const uint32_t row = bn * a.HW + hw;
-      off16 = row * row16;
-      dv = __ldg(a.depth_t + (size_t)row * a.D + d);
-    } else {
-      off16 = static_cast<uint32_t>(p) * row16;
-      dv = 1.0f;
-    }
-  };
+  int before = -1;
+  if (lane == 0 && i0 > 0) before = __ldg(&a.rec[i0 - 1].x);
+  uint32_t H[kW], HV[kW];                                   // heads (cell differs from its predecessor), valid heads
+#pragma unroll
+  for (int w = 0; w < kW; ++w) {
+    int prev = __shfl_up_sync(0xffffffffu, cell[w], 1);
+    if (lane == 0) prev = before;
+    before = __shfl_sync(0xffffffffu, cell[w], 31);         // predecessor of the next word's lane 0
+    H[w] = __ballot_sync(0xffffffffu, cell[w] != prev);
+    HV[w] = H[w] & __ballot_sync(0xffffffffu, cell[w] >= 0);
+  }
+  // ---- walker of this lane: records [r0, end) ----
+  const int g = lane / L, sub = lane % L;
+  const int lo_bit = g * S;                                  // first record of the walker's share
+  int r0, end;
   {
-    uint32_t o0 = 0, o1 = 0;
-    float d0 = 0.f, d1 = 0.f;
-    const bool own0 = lane >= h0 && lane < nv, own1 = lane < tail;
-    if (own0) record(pt, o0, d0);
-    if (own1) record(npt, o1, d1);
-    if (own0) { offs[lane - h0] = o0; deps[lane - h0] = d0; }
-    if (own1) { offs[nv - h0 + lane] = o1; deps[nv - h0 + lane] = d1; }
-    s_cell[warp][lane] = cell;
+    uint32_t m;
+    if (S >= 32) {                                           // share = whole words
+      r0 = NR;
+#pragma unroll
+      for (int w = (S / 32) - 1; w >= 0; --w) {
+        const uint32_t b = HV[(lo_bit >> 5) + w < kW ? (lo_bit >> 5) + w : 0];
+        if (b) r0 = ((lo_bit >> 5) + w) * 32 + __ffs(b) - 1;
+      }
+      m = r0 < NR ? 1u : 0u;
+    } else {
+      const uint32_t mask = ((S == 32) ? 0xffffffffu : ((1u << (S & 31)) - 1u)) << (lo_bit & 31);
+      m = 0u;
+#pragma unroll
+      for (int w = 0; w < kM; ++w) if ((lo_bit >> 5) == w) m = HV[w] & mask;
+      r0 = (lo_bit & ~31) + __ffs(m) - 1;
+    }
+    end = first_bit_from<kW>(H, lo_bit + S);
+    if (!m) { r0 = 0; end = 0; }
+  }
+  const int n_g = end - r0;
+  const bool overflow = n_g > 0 && end == NR;                // the last interval runs past the look-ahead
+  const int n_max = __reduce_max_sync(0xffffffffu, n_g);
+  if (n_max == 0) return;                                    // earlier warps own all of it
+  const int hi = __reduce_max_sync(0xffffffffu, end);
+  const int lo = __reduce_min_sync(0xffffffffu, n_g > 0 ? r0 : NR);
+
+  // ---- stage the records the walkers will touch ----
+  const uint32_t row16 = static_cast<uint32_t>(a.C) >> 2;    // 16-byte units per feature row
+#pragma unroll
+  for (int w = 0; w < kW; ++w) {
+    const int r = w * 32 + lane;
+    if (r >= lo && r < hi && cell[w] >= 0) {
+      uint32_t off16;
+      float dv;
+      if (kFused) {
+        uint32_t bn, rem, d, hw;
+        a.div_dhw.divmod(static_cast<uint32_t>(pt[w]), bn, rem);
+        a.div_hw.divmod(rem, d, hw);
+        off16 = (bn * static_cast<uint32_t>(a.HW) + hw) * row16;
+        dv = load_as_float(a.depth, (size_t)bn * a.depth_bs + rem, a.depth_dtype);
+      } else {
+        off16 = static_cast<uint32_t>(pt[w]) * row16;
+        dv = 1.0f;
+      }
+      // a walker's first record opens its first interval: nothing to close there
+      bool head = (H[w] >> lane) & 1u;
+      if (w < kM) {
+        const int gs = r / S;                                 // walker whose share holds r
+        uint32_t share = HV[w];
+        if (S < 32) share &= ((1u << (S & 31)) - 1u) << ((gs * S) & 31);
+        bool first_of_share = (share & (0u - share)) == (1u << lane);
+        if (S > 32) first_of_share = first_of_share && (w == 0 || HV[0] == 0u);
+        if (first_of_share) head = false;
+      }
+      s_rec[warp][r] = make_uint2(off16 | (head ? 0x80000000u : 0u), __float_as_uint(dv));
+      s_cell[warp][r] = cell[w];
+    }
+  }
+  __syncwarp();
+  // padding record of the walker: its own last record with weight zero (re-gathers a row it has
+  // already summed, adds 0 * row), for the steps after its end while other walkers still run
+  if (sub == 0) {
+    uint2 pad = make_uint2(0u, 0u);
+    if (n_g > 0) pad = make_uint2(s_rec[warp][end - 1].x & 0x7fffffffu, 0u);
+    s_rec[warp][NR + g] = pad;
   }
   __syncwarp();
 
-  // ---- walk: software pipeline over groups of kU records ----
-  const uint32_t heads = hb >> h0;                           // bit r: record r starts an interval (bit 0 set)
-  int cur = s_cell[warp][h0];
-  V acc;
-  vec_zero<kVec>(acc);
-  auto issue = [&](int r, V (&f)[kU]) {
-    const uint4 o4 = s_off[warp][r >> 2];
-    f[0] = gather(o4.x);
-    f[1] = gather(o4.y);
-    f[2] = gather(o4.z);
-    f[3] = gather(o4.w);
+  const uint32_t vsub = (static_cast<int>(sub) < a.nact) ? sub : 0u;   // idle lanes shadow lane 0, never store
+  const bool storer = n_g > 0 && static_cast<int>(sub) < a.nact;
+  const char* src = reinterpret_cast<const char*>((kFused ? a.feat_t : a.x) + vsub * 4);
+  const char* src2 = reinterpret_cast<const char*>((kFused ? a.feat_t : a.x) + 4 * L * kNP + vsub * 2);
+  float* out = a.bev + vsub * 4;
+  float* out2 = a.bev + 4 * L * kNP + vsub * 2;
+  const uint2* recs = s_rec[warp];
+
+  float4 acc[kNP > 0 ? kNP : 1];
+  float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int p = 0; p < kNP; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = (n_g > 0) ? s_cell[warp][r0] : 0;
+  auto close = [&](int next_cell) {
+    if (storer) {
+      float* o = out + (size_t)cur * a.C;
+#pragma unroll
+      for (int p = 0; p < kNP; ++p) *reinterpret_cast<float4*>(o + p * 4 * L) = acc[p];
+      if (kT2) *reinterpret_cast<float2*>(out2 + (size_t)cur * a.C) = acc2;
+    }
+#pragma unroll
+    for (int p = 0; p < kNP; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc2 = make_float2(0.f, 0.f);
+    cur = next_cell;
   };
-  auto consume = [&](int r, const V (&f)[kU]) {
-    const float4 d4 = s_dep[warp][r >> 2];
-    const float d[kU] = {d4.x, d4.y, d4.z, d4.w};
-    const uint32_t hm = (r < 32) ? ((heads >> r) & 0xfu) : 0u;
+
+  for (int t0 = 0; t0 < n_max; t0 += U) {
+    uint2 rc[U];
+    int ri[U];
+    float4 f[U][kNP > 0 ? kNP : 1];
+    float2 f2[U];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      if (((hm >> u) & 1u) && (r + u) > 0) {                 // warp-uniform: a new interval starts
-        if (active) out[(size_t)cur * nact] = acc;
-        vec_zero<kVec>(acc);
-        cur = s_cell[warp][h0 + r + u];
-      }
-      vec_fma(d[u], f[u], acc);
-    }
-  };
-  const int n_full = n_rec & ~(kU - 1);
-  if (n_full > 0) {
-    V f[kS][kU];
+    for (int u = 0; u < U; ++u) {
+      ri[u] = (t0 + u < n_g) ? r0 + t0 + u : NR + g;
+      rc[u] = recs[ri[u]];
+      const size_t byte = (size_t)(rc[u].x & 0x7fffffffu) << 4;
 #pragma unroll
-    for (int st = 0; st < kS - 1; ++st)
-      if (st * kU < n_full) issue(st * kU, f[st]);
-    for (int r0 = 0; r0 < n_full; r0 += kS * kU) {
+      for (int p = 0; p < kNP; ++p) f[u][p] = __ldg(reinterpret_cast<const float4*>(src + byte) + p * L);
+      if (kT2) f2[u] = __ldg(reinterpret_cast<const float2*>(src2 + byte));
+    }
 #pragma unroll
-      for (int st = 0; st < kS; ++st) {
-        const int r = r0 + st * kU;
-        if (r < n_full) {
-          if (r + (kS - 1) * kU < n_full) issue(r + (kS - 1) * kU, f[(st + kS - 1) % kS]);
-          consume(r, f[st]);
-        }
-      }
+    for (int u = 0; u < U; ++u) {
+      if (static_cast<int>(rc[u].x) < 0) close(s_cell[warp][ri[u]]);
+      const float dv = __uint_as_float(rc[u].y);
+#pragma unroll
+      for (int p = 0; p < kNP; ++p) f4_fma(dv, f[u][p], acc[p]);
+      if (kT2) { acc2.x = fmaf(dv, f2[u].x, acc2.x); acc2.y = fmaf(dv, f2[u].y, acc2.y); }
     }
-  }
-  for (int r = n_full; r < n_rec; ++r) {                     // at most kU - 1 records
-    const V f = gather(offs[r]);
-    if (r < 32 && ((heads >> r) & 1u) && r > 0) {
-      if (active) out[(size_t)cur * nact] = acc;
-      vec_zero<kVec>(acc);
-      cur = s_cell[warp][h0 + r];
-    }
-    vec_fma(deps[r], f, acc);
   }
   // ---- an interval longer than the look-ahead (adversarial inputs): follow it to its end ----
-  if (tail == 32) {
-    for (long long j = i0 + 2 * kPoolChunk; j < a.P; ++j) {
-      if (__ldg(a.sorted_cells + j) != last_cell) break;
-      uint32_t o;
+  if (overflow) {
+    for (long long j = i0 + NR; j < a.P; ++j) {
+      const int2 r = __ldg(a.rec + j);
+      if (r.x != cur) break;
+      uint32_t off16;
       float dv;
-      record(__ldg(a.sorted_points + j), o, dv);
-      vec_fma(dv, gather(o), acc);
+      if (kFused) {
+        uint32_t bn, rem, d, hw;
+        a.div_dhw.divmod(static_cast<uint32_t>(r.y), bn, rem);
+        a.div_hw.divmod(rem, d, hw);
+        off16 = (bn * static_cast<uint32_t>(a.HW) + hw) * row16;
+        dv = load_as_float(a.depth, (size_t)bn * a.depth_bs + rem, a.depth_dtype);
+      } else {
+        off16 = static_cast<uint32_t>(r.y) * row16;
+        dv = 1.0f;
+      }
+      const size_t byte = (size_t)off16 << 4;
+#pragma unroll
+      for (int p = 0; p < kNP; ++p) f4_fma(dv, __ldg(reinterpret_cast<const float4*>(src + byte) + p * L), acc[p]);
+      if (kT2) {
+        const float2 t2 = __ldg(reinterpret_cast<const float2*>(src2 + byte));
+        acc2.x = fmaf(dv, t2.x, acc2.x); acc2.y = fmaf(dv, t2.y, acc2.y);
+      }
     }
   }
-  if (active) out[(size_t)cur * nact] = acc;
-  if (lane == 0) phase_stamp_any(2, warp * 2 + 1);
+  if (n_g > 0) close(0);
 }
 
 // --------------------------------------------------------------------------
@@ -443,7 +469,7 @@ pool_dense_bwd_nhwc_kernel(const float4* __restrict__ dbev, const int32_t* __res
     div_g.divmod(static_cast<uint32_t>(e), p, chunk);
     const int32_t cell = __ldg(cells + p);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cell >= 0) v = ldg_f4(dbev + (size_t)cell * G + chunk);
+    if (cell >= 0) v = __ldg(dbev + (size_t)cell * G + chunk);
     dx[e] = v;
   }
 }
@@ -451,127 +477,181 @@ pool_dense_bwd_nhwc_kernel(const float4* __restrict__ dbev, const int32_t* __res
 // --------------------------------------------------------------------------
 // K5 fused backward, channels-innermost dBEV.
 //
-// A warp owns one pixel (bn, h, w): its context vector stays in registers while
-// the warp walks the pixel's D depth bins.  kLanes lanes (a power of two >= C/4)
-// cooperate on one point, 32/kLanes points sit side by side in the warp and
-// kUnroll such steps are issued back to back, so kUnroll*32/kLanes voxel-gradient
-// lines are in flight per warp.  For every kept point the voxel gradient g (one
-// contiguous line of the channels-innermost dBEV) is gathered once and used twice:
+// A walker of L lanes owns one PIXEL (bn, h, w): its context vector stays in
+// registers (as float64) while it visits the pixel's depth bins; the G = 32/L
+// walkers of a warp are G consecutive image rows h of one image column (bn, w),
+// and the warps of a CTA are the column's row groups x slices of the depth axis.
+// Along a camera ray neighbouring rows fall into the same BEV cell (Z is
+// collapsed), so the G gathers of one warp instruction mostly hit the same
+// line.  For every kept point the voxel gradient g (one contiguous line of the
+// channels-innermost dBEV) is gathered once and used twice:
 //     d_depth[d] = <g, feat>      d_feat += depth[d] * g
 // Only OCCUPIED voxels of dBEV are ever read.  <g, feat> has C terms of order one
-// that cancel, so it is accumulated in float64 and the kUnroll partial dots of a
-// lane are reduced together with a transposed butterfly (2*kUnroll shuffles
-// instead of kUnroll*log2(kLanes)).  The warps of a CTA are the fH pixels of one
-// image column (bn, w): along a camera ray they fall into the same BEV cells
-// (Z is collapsed), so the column's voxel lines are fetched from L2 once and
-// re-used out of L1.  There is no CTA-wide phase and no atomics: warps run
-// independently and results are bit-reproducible.
+// that cancel, so it is accumulated in float64 -- but without the float32 ->
+// float64 conversion instruction, which runs at a sixteenth of the FMA rate on
+// this part and was the limiter of the previous version of this kernel: the 32
+// bits of g are re-packed with three integer operations into the float64 whose
+// value is g * 2^-896 exactly (sign | exponent | mantissa shifted by three bits;
+// zero stays zero, denormals stay exact), and the finished dot is scaled back by
+// 2^896.  The kU partial dots of a lane are reduced together with a transposed
+// butterfly.  There are no atomics: the depth slices' partial d_feat meet in
+// shared memory in a fixed order, results are bit-reproducible.
+// A non-finite upstream gradient still reaches the outputs: d_feat sees it
+// through the float32 FMA, and a walker whose d_feat partial is not finite
+// writes NaN to the d_depth bins of its slice.
 // --------------------------------------------------------------------------
 struct PoolBwdArgs {
-  const float4* dbev;       // (n_cells, G)
-  const float* depth_t;     // (BN*HW, D)
-  const float4* feat_t;     // (BN*HW, G)
+  const float* dbev;        // (n_cells, C)
+  const void* depth;        // (BN, D*HW) depth distribution (softmax: probabilities), batch stride depth_bs
+  long long depth_bs;
+  int depth_dtype;
+  const float* feat_t;      // (BN*HW, C)
   const int32_t* cells;     // (BN, D, fH, fW)
   void* ddepth;             // (BN, D, fH, fW) with batch stride ddepth_bs: d_depth, or d_logits when softmax
   void* dfeat;              // (BN, C, fH, fW) with batch stride dfeat_bs
   long long ddepth_bs, dfeat_bs;
   int out_dtype;            // LssDtype of both outputs
-  int softmax;              // 1: depth_t = softmax(logits); emit d_logits = p * (d_depth - sum_d p * d_depth)
-  int D, fH, fW, C, G;
-  int n_pix;                // BN * fH * fW
-  FastDiv div_fh, div_fw;
+  int softmax;              // 1: depth = softmax(logits); emit d_logits = p * (d_depth - sum_d p * d_depth)
+  int D, fH, fW, C, BN;
+  int nact;                 // lanes of a walker that own channels
+  int rg_warps;             // warps of a CTA along the rows (power of two <= 8); the other 8/rg_warps slice D
+  int d_per_slice;
+  int row_blocks;           // CTAs per image column: ceil(fH / (G * rg_warps))
 };
 
-#ifndef LSS_BWD_THREADS
-#define LSS_BWD_THREADS 256
-#endif
-constexpr int kBwdThreads = LSS_BWD_THREADS;
+constexpr int kBwdThreads = 256;
 constexpr int kBwdWarps = kBwdThreads / 32;
-constexpr int kBwdChunk = 128;   // depth bins staged per warp at a time
+constexpr int kBwdChunk = 32;    // depth bins staged per walker at a time
+constexpr int kBwdMaxD = 128;    // softmax backward keeps a pixel's d_depth in shared memory
 
-// kGeneral = false: float32 gradients, no fused softmax (the plain K5); true: output dtype and the
-// fused softmax backward are run-time options (kept out of the plain kernel's inner loop)
-template <int kLanes, bool kGeneral>
+// the float64 whose value is x * 2^-896 (exact for every finite float32, zero -> zero)
+__device__ __forceinline__ double f32_as_scaled_f64(float x) {
+  const int b = __float_as_int(x);
+  return __hiloint2double((b >> 3) & static_cast<int>(0x8fffffffu), b << 29);
+}
+
+template <int L, int kNP, bool kT2, bool kGeneral>
 __global__ void __launch_bounds__(kBwdThreads, LSS_BWD_MINB)
-liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
-  constexpr int kPts = 32 / kLanes;                 // points per warp step
-  constexpr int kUnroll = kLanes >= 8 ? 8 : kLanes; // steps in flight
-  constexpr int kRound = kPts * kUnroll;            // depth bins per round
-  constexpr int kLog = kLanes == 32 ? 5 : kLanes == 16 ? 4 : kLanes == 8 ? 3 : 2;
-  constexpr int kLogU = kUnroll == 8 ? 3 : 2;
-  static_assert(kBwdChunk % kRound == 0, "chunk must hold whole rounds");
-  __shared__ int2 s_cd[kBwdWarps][kBwdChunk];       // {output cell, depth bits} of the staged bins
-  __shared__ float s_dd[kGeneral ? kBwdWarps : 1][kGeneral ? kBwdChunk : 1];   // d_depth of the pixel (softmax backward)
+liftsplat_bwd_kernel(PoolBwdArgs a) {
+  constexpr int G = 32 / L;                     // pixels (walkers) per warp
+  constexpr int U = 4;                          // depth bins per round
+  constexpr int kLog = L == 32 ? 5 : L == 16 ? 4 : L == 8 ? 3 : L == 4 ? 2 : L == 2 ? 1 : 0;
+  constexpr int kLogU = kLog < 2 ? kLog : 2;    // exchange levels that halve the live dots
+  constexpr int kV = 4 * kNP + (kT2 ? 2 : 0);   // channels per lane
+  static_assert(kBwdChunk % U == 0, "chunk must hold whole rounds");
+  __shared__ int2 s_cd[kBwdWarps][G][kBwdChunk];             // {output cell, depth bits (0 if dropped)}
+  __shared__ float s_df[kBwdWarps][G * (L * kV)];            // the warp's partial d_feat
+  __shared__ float s_dd[kGeneral ? G * kBwdWarps : 1][kGeneral ? kBwdMaxD : 1];   // d_depth of the CTA's pixels (softmax)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // pixel of this warp: h fastest, so a CTA is one image column (bn, w) when fH == 8
-  const uint32_t q = blockIdx.x * kBwdWarps + warp;
-  if (q >= static_cast<uint32_t>(a.n_pix)) return;
-  uint32_t t, h, bn, w;
-  a.div_fh.divmod(q, t, h);
-  a.div_fw.divmod(t, bn, w);
+  const int g = lane / L, sub = lane % L;
+  // CTA -> (image column, block of rows); warp -> (row group, depth slice)
+  const int col = blockIdx.x / a.row_blocks, rb = blockIdx.x - col * a.row_blocks;
+  const int bn = col / a.fW, w = col - bn * a.fW;
+  const int rg = warp % a.rg_warps, slice = warp / a.rg_warps;
+  const int h = (rb * a.rg_warps + rg) * G + g;
+  const bool pix_ok = h < a.fH;
   const int HW = a.fH * a.fW;
-  const uint32_t pix = bn * HW + h * a.fW + w;
-  const int grp = lane / kLanes, sub = lane % kLanes;
-  const bool lane_active = sub < a.G;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  // which of the kUnroll dots this lane ends up holding after the transposed butterfly
+  const int hw = (pix_ok ? h : 0) * a.fW + w;
+  const int d_lo = slice * a.d_per_slice;
+  const int d_hi = min(a.D, d_lo + a.d_per_slice);
+  const bool lane_act = sub < a.nact;
+  const int vsub = lane_act ? sub : 0;
+
+  // the pixel's context vector, float64
+  double fd[kV > 0 ? kV : 1];
+  {
+    const float* frow = a.feat_t + ((size_t)bn * HW + hw) * a.C;
+#pragma unroll
+    for (int p = 0; p < kNP; ++p) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(frow + vsub * 4) + p * L);
+      fd[4 * p + 0] = f.x; fd[4 * p + 1] = f.y; fd[4 * p + 2] = f.z; fd[4 * p + 3] = f.w;
+    }
+    if (kT2) {
+      const float2 f = __ldg(reinterpret_cast<const float2*>(frow + 4 * L * kNP + vsub * 2));
+      fd[4 * kNP] = f.x; fd[4 * kNP + 1] = f.y;
+    }
+    if (!lane_act || !pix_ok) {
+#pragma unroll
+      for (int v = 0; v < kV; ++v) fd[v] = 0.0;
+    }
+  }
+  float acc[kV > 0 ? kV : 1];
+#pragma unroll
+  for (int v = 0; v < kV; ++v) acc[v] = 0.f;
+
+  // which of the U dots this lane ends up holding after the transposed butterfly
   int my_u = 0;
 #pragma unroll
   for (int k = 0; k < kLogU; ++k)
-    if (sub & (kLanes >> (k + 1))) my_u += kUnroll >> (k + 1);
-  const bool writer = (sub & ((kLanes >> kLogU) - 1)) == 0;
-  const uint32_t G = static_cast<uint32_t>(a.G);
-  const float4* gbase = a.dbev + sub;                 // this lane's float4 column of every voxel line
-  const float4 f = lane_active ? ldg_f4(a.feat_t + pix * G + sub) : zero4;
-  const double fx = f.x, fy = f.y, fz = f.z, fw = f.w;
-  float4 acc = zero4;
-  int2* cd = s_cd[warp];
-  const size_t col = (size_t)h * a.fW + w;            // offset of the pixel inside a (fH, fW) slice
+    if (sub & (L >> (k + 1))) my_u += U >> (k + 1);
+  const bool writer = (kLog == kLogU) ? true : (sub & ((L >> kLogU) - 1)) == 0;
+  constexpr int kDots = (kLog >= 2) ? 1 : (kLog == 1 ? 2 : 4);   // dots a writer holds per round
 
-  for (int dc = 0; dc < a.D; dc += kBwdChunk) {
-    const int nd = min(kBwdChunk, a.D - dc);
-    const int nd_pad = (nd + kRound - 1) / kRound * kRound;
+  const float* gsrc = a.dbev + vsub * 4;
+  const float* gsrc2 = a.dbev + 4 * L * kNP + vsub * 2;
+  const size_t pbase = (size_t)bn * a.D * HW + hw;           // cells index of (bn, d = 0, h, w)
+  const size_t dbase = (size_t)bn * a.depth_bs + hw;
+  int2 (*cd)[kBwdChunk] = s_cd[warp];
+
+  for (int dc = d_lo; dc < d_hi; dc += kBwdChunk) {
+    const int nd = min(kBwdChunk, d_hi - dc);
     __syncwarp();
-    for (int l = lane; l < nd_pad; l += 32) {
-      int2 v = make_int2(-1, 0);                      // padding = dropped point
-      if (l < nd) {
-        const int d = dc + l;
-        v.x = __ldg(a.cells + ((size_t)bn * a.D + d) * HW + col);
-        v.y = __float_as_int(__ldg(a.depth_t + (size_t)pix * a.D + d));
+    // stage {cell, depth} of the warp's G pixels x nd bins: lane -> (pixel e / 32... ) one bin each
+#pragma unroll
+    for (int e = lane; e < G * kBwdChunk; e += 32) {
+      const int gp = e / kBwdChunk, dl = e - gp * kBwdChunk;
+      int2 v = make_int2(-1, 0);                            // padding / dropped point: weight zero
+      const int hh = h - g + gp;                            // row of walker gp
+      if (dl < nd && hh < a.fH) {
+        const long long o = (long long)(dc + dl) * HW + (long long)(gp - g) * a.fW;
+        v.x = __ldg(a.cells + (long long)pbase + o);
+        if (v.x >= 0) v.y = __float_as_int(load_as_float(a.depth, (size_t)((long long)dbase + o), a.depth_dtype));
       }
-      cd[l] = v;
+      cd[gp][dl] = v;
     }
     __syncwarp();
-    for (int d0 = 0; d0 < nd_pad; d0 += kRound) {
-      float4 g[kUnroll];
-      float dv[kUnroll];
+    const int nd_pad = (nd + U - 1) / U * U;
+    for (int d0 = 0; d0 < nd_pad; d0 += U) {
+      float4 gq[U][kNP > 0 ? kNP : 1];
+      float2 g2[U];
+      float dv[U];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int2 v = cd[d0 + u * kPts + grp];
+      for (int u = 0; u < U; ++u) {
+        const int2 v = cd[g][d0 + u];
         dv[u] = __int_as_float(v.y);
-        const uint32_t off = static_cast<uint32_t>(v.x) * G;   // n_cells * G < 2^31 (checked by the host)
-        g[u] = (v.x >= 0 && lane_active) ? ldg_f4(gbase + off) : zero4;
-      }
-      double dot[kUnroll];
+        const size_t off = (size_t)max(v.x, 0) * a.C;       // dropped: any valid line, weight zero
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        double s = static_cast<double>(g[u].x) * fx;
-        s = fma(static_cast<double>(g[u].y), fy, s);
-        s = fma(static_cast<double>(g[u].z), fz, s);
-        s = fma(static_cast<double>(g[u].w), fw, s);
-        dot[u] = s;
-        acc.x = fmaf(dv[u], g[u].x, acc.x);
-        acc.y = fmaf(dv[u], g[u].y, acc.y);
-        acc.z = fmaf(dv[u], g[u].z, acc.z);
-        acc.w = fmaf(dv[u], g[u].w, acc.w);
+        for (int p = 0; p < kNP; ++p) gq[u][p] = __ldg(reinterpret_cast<const float4*>(gsrc + off) + p * L);
+        if (kT2) g2[u] = __ldg(reinterpret_cast<const float2*>(gsrc2 + off));
       }
-      // transposed butterfly: halve the number of live values at every exchange
+      double dot[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double s = 0.0;
+#pragma unroll
+        for (int p = 0; p < kNP; ++p) {
+          const float gv[4] = {gq[u][p].x, gq[u][p].y, gq[u][p].z, gq[u][p].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s = fma(f32_as_scaled_f64(gv[k]), fd[4 * p + k], s);
+            acc[4 * p + k] = fmaf(dv[u], gv[k], acc[4 * p + k]);
+          }
+        }
+        if (kT2) {
+          s = fma(f32_as_scaled_f64(g2[u].x), fd[4 * kNP], s);
+          s = fma(f32_as_scaled_f64(g2[u].y), fd[4 * kNP + 1], s);
+          acc[4 * kNP] = fmaf(dv[u], g2[u].x, acc[4 * kNP]);
+          acc[4 * kNP + 1] = fmaf(dv[u], g2[u].y, acc[4 * kNP + 1]);
+        }
+        dot[u] = s;
+      }
+      // transposed butterfly over the walker's L lanes: halve the number of live dots per exchange
 #pragma unroll
       for (int k = 0; k < kLog; ++k) {
-        const int o = kLanes >> (k + 1);
+        const int o = L >> (k + 1);
         if (k < kLogU) {
-          const int half = kUnroll >> (k + 1);
+          const int half = U >> (k + 1);
           const bool upper = (sub & o) != 0;
 #pragma unroll
           for (int i = 0; i < half; ++i) {
@@ -583,46 +663,88 @@ liftsplat_bwd_nhwc_kernel(PoolBwdArgs a) {
           dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
         }
       }
-      const int d = dc + d0 + my_u * kPts + grp;
-      if (writer && d < a.D) {
-        const size_t o = (size_t)bn * a.ddepth_bs + (size_t)d * HW + col;
-        if (!kGeneral) reinterpret_cast<float*>(a.ddepth)[o] = static_cast<float>(dot[0]);
-        else if (a.softmax) s_dd[warp][d] = static_cast<float>(dot[0]);   // D <= kBwdChunk (host)
-        else store_from_float(a.ddepth, o, static_cast<float>(dot[0]), a.out_dtype);
+      if (writer && pix_ok) {
+#pragma unroll
+        for (int i = 0; i < kDots; ++i) {
+          const int dl = d0 + my_u + i;
+          if (dl < nd) {
+            const int d = dc + dl;
+            // 2^896: back from the scaled domain; dropped points (weight zero, foreign line) give 0
+            float r = static_cast<float>(dot[i] * 5.2829453113566525e269);
+            if (cd[g][dl].x < 0) r = 0.f;
+            const size_t o = (size_t)bn * a.ddepth_bs + (size_t)d * HW + hw;
+            if (!kGeneral) reinterpret_cast<float*>(a.ddepth)[o] = r;
+            else if (a.softmax) s_dd[rg * G + g][d] = r;      // D <= kBwdMaxD (host)
+            else store_from_float(a.ddepth, o, r, a.out_dtype);
+          }
+        }
       }
+    }
+  }
+  // a non-finite gradient line shows in the float32 partial d_feat: poison this slice's d_depth
+  {
+    float chk = 0.f;
+#pragma unroll
+    for (int v = 0; v < kV; ++v) chk += fabsf(acc[v]);
+    const bool bad = !(chk <= 3.4028235e38f);
+    uint32_t bm = __ballot_sync(0xffffffffu, bad);
+    if (L < 32) bm = (bm >> (g * L)) & ((1u << (L & 31)) - 1u);
+    if (bm && pix_ok) {
+      const float qnan = __int_as_float(0x7fc00000);
+      for (int d = d_lo + sub; d < d_hi; d += L) {
+        const size_t o = (size_t)bn * a.ddepth_bs + (size_t)d * HW + hw;
+        if (!kGeneral) reinterpret_cast<float*>(a.ddepth)[o] = qnan;
+        else if (a.softmax) s_dd[rg * G + g][d] = qnan;
+        else store_from_float(a.ddepth, o, qnan, a.out_dtype);
+      }
+    }
+  }
+  // ---- d_feat: the depth slices' partials meet in shared memory, summed in slice order ----
+  {
+    float* mine = s_df[warp] + g * (L * kV);
+#pragma unroll
+    for (int p = 0; p < kNP; ++p)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mine[p * 4 * L + sub * 4 + k] = acc[4 * p + k];
+    if (kT2) { mine[4 * L * kNP + sub * 2] = acc[4 * kNP]; mine[4 * L * kNP + sub * 2 + 1] = acc[4 * kNP + 1]; }
+  }
+  __syncthreads();
+  {
+    const int n_slices = kBwdWarps / a.rg_warps;
+    const int rows = a.rg_warps * G;                         // pixel rows of this CTA
+    // consecutive threads -> consecutive rows (the contiguous direction of the output is w, which
+    // a column CTA does not span), channels outer
+    for (int i = threadIdx.x; i < rows * a.C; i += kBwdThreads) {
+      const int r = i % rows, c = i / rows;
+      const int hh = rb * rows + r;
+      if (hh >= a.fH) continue;
+      const int wg = r / G, gg = r - wg * G;                 // row group (warp along rows), walker
+      float s = 0.f;
+      for (int sl = 0; sl < n_slices; ++sl) s += s_df[sl * a.rg_warps + wg][gg * (L * kV) + c];
+      const size_t o = (size_t)bn * a.dfeat_bs + (size_t)c * HW + (size_t)hh * a.fW + w;
+      if (!kGeneral) reinterpret_cast<float*>(a.dfeat)[o] = s;
+      else store_from_float(a.dfeat, o, s, a.out_dtype);
     }
   }
   if (kGeneral && a.softmax) {
     // softmax backward (reference: autograd of x.softmax(dim=1), src/modules.py:77), fused:
-    // d_logit[d] = p[d] * (d_depth[d] - sum_d' p[d'] * d_depth[d'])
-    __syncwarp();
-    double sp = 0.0;
-    for (int l = lane; l < a.D; l += 32) sp += static_cast<double>(__int_as_float(cd[l].y)) * static_cast<double>(s_dd[warp][l]);
+    // d_logit[d] = p[d] * (d_depth[d] - sum_d' p[d'] * d_depth[d']); one warp per pixel row
+    const int rows = a.rg_warps * G;
+    for (int r = warp; r < rows; r += kBwdWarps) {
+      const int hh = rb * rows + r;
+      if (hh >= a.fH) continue;
+      const size_t pix = (size_t)hh * a.fW + w;
+      double sp = 0.0;
+      for (int d = lane; d < a.D; d += 32)
+        sp += static_cast<double>(load_as_float(a.depth, (size_t)bn * a.depth_bs + (size_t)d * HW + pix, a.depth_dtype)) *
+              static_cast<double>(s_dd[r][d]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
-    const float spf = static_cast<float>(sp);
-    for (int l = lane; l < a.D; l += 32)
-      store_from_float(a.ddepth, (size_t)bn * a.ddepth_bs + (size_t)l * HW + col,
-                       __int_as_float(cd[l].y) * (s_dd[warp][l] - spf), a.out_dtype);
-  }
-  // fold the kPts point-groups of the warp together
-#pragma unroll
-  for (int o = kLanes; o < 32; o <<= 1) {
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-  }
-  if (grp == 0 && lane_active) {
-    const size_t df = (size_t)bn * a.dfeat_bs + (size_t)(sub * 4) * HW + col;
-    if (!kGeneral) {
-      float* o = reinterpret_cast<float*>(a.dfeat) + df;
-      o[0] = acc.x; o[HW] = acc.y; o[2 * (size_t)HW] = acc.z; o[3 * (size_t)HW] = acc.w;
-    } else {
-      store_from_float(a.dfeat, df, acc.x, a.out_dtype);
-      store_from_float(a.dfeat, df + HW, acc.y, a.out_dtype);
-      store_from_float(a.dfeat, df + 2 * (size_t)HW, acc.z, a.out_dtype);
-      store_from_float(a.dfeat, df + 3 * (size_t)HW, acc.w, a.out_dtype);
+      for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+      const float spf = static_cast<float>(sp);
+      for (int d = lane; d < a.D; d += 32) {
+        const float pd = load_as_float(a.depth, (size_t)bn * a.depth_bs + (size_t)d * HW + pix, a.depth_dtype);
+        store_from_float(a.ddepth, (size_t)bn * a.ddepth_bs + (size_t)d * HW + pix, pd * (s_dd[r][d] - spf), a.out_dtype);
+      }
     }
   }
 }

@@ -40,6 +40,18 @@ def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _call(dev, name: str, *args) -> None:
+    """One C-ABI call with ``dev`` as the current CUDA device.  The library launches on the current
+    device (d_* pointers are "device pointers on the current CUDA device", include/lss_b200.h); the
+    reference scripts move the model with ``.to(f'cuda:{gpuid}')`` and never call set_device
+    (train.py:34, predict.py:35), so the tensors' device is what counts, not torch's current one."""
+    if torch.cuda.current_device() == dev.index:
+        _abi.call(name, *args)
+    else:
+        with torch.cuda.device(dev):
+            _abi.call(name, *args)
+
+
 def _need_cuda(*tensors: torch.Tensor) -> torch.device:
     dev = None
     for t in tensors:
@@ -132,7 +144,7 @@ def camera_prep(rots, intrins, post_rots):
     n = rots.numel() // 9
     ipr = torch.empty_like(post_rots)
     comb = torch.empty_like(rots)
-    _abi.call("lss_camera_prep", _ptr(rots), _ptr(intrins), _ptr(post_rots), n, _ptr(ipr),
+    _call(dev, "lss_camera_prep", _ptr(rots), _ptr(intrins), _ptr(post_rots), n, _ptr(ipr),
               _ptr(comb), _stream(dev))
     return ipr, comb
 
@@ -161,7 +173,7 @@ def geometry(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: Grid
     if want_kept:
         out["kept"] = torch.empty(P, dtype=torch.uint8, device=dev)
     g = grid.c()
-    _abi.call("lss_geometry_rank", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
+    _call(dev, "lss_geometry_rank", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
               _ptr(_f32c(inv_post_rots)), _ptr(_f32c(post_trans)), _ptr(_f32c(combine)),
               _ptr(_f32c(trans)), g, shape, _ptr(out.get("geom")), _ptr(out.get("coords")),
               _ptr(out.get("kept")), _ptr(out["ranks"]), _ptr(out["cells"]), _stream(dev))
@@ -180,7 +192,7 @@ def quantize_rank(geom: torch.Tensor, grid: GridSpec, B: int, want_coords=False,
         out["coords"] = torch.empty((P, 3), dtype=torch.int32, device=dev)
     if want_kept:
         out["kept"] = torch.empty(P, dtype=torch.uint8, device=dev)
-    _abi.call("lss_quantize_rank", _ptr(geom), grid.c(), B, P, _ptr(out.get("coords")),
+    _call(dev, "lss_quantize_rank", _ptr(geom), grid.c(), B, P, _ptr(out.get("coords")),
               _ptr(out.get("kept")), _ptr(out["ranks"]), _ptr(out["cells"]), _stream(dev))
     return out
 
@@ -194,7 +206,7 @@ def sort_ranks(ranks: torch.Tensor, n_cells: int):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     sk = torch.empty_like(ranks)
     sp = torch.empty_like(ranks)
-    _abi.call("lss_sort_ranks", _ptr(ranks), P, n_cells, _ptr(sk), _ptr(sp), _ptr(ws), nbytes,
+    _call(dev, "lss_sort_ranks", _ptr(ranks), P, n_cells, _ptr(sk), _ptr(sp), _ptr(ws), nbytes,
               _stream(dev))
     return sk, sp
 
@@ -208,7 +220,7 @@ def intervals(sorted_ranks: torch.Tensor, grid: GridSpec, B: int, want_last_mask
     counts = torch.zeros(2, dtype=torch.int32, device=dev)
     last = torch.empty(P, dtype=torch.uint8, device=dev) if want_last_mask else None
     sorted_cells = torch.empty(P, dtype=torch.int32, device=dev)
-    _abi.call("lss_intervals", _ptr(sorted_ranks), P, grid.c(), B, _ptr(last), _ptr(sorted_cells),
+    _call(dev, "lss_intervals", _ptr(sorted_ranks), P, grid.c(), B, _ptr(last), _ptr(sorted_cells),
               _ptr(cell_range), _ptr(counts), _stream(dev))
     return cell_range, counts, last, sorted_cells
 
@@ -232,14 +244,23 @@ class Plan:
     fH: int
     fW: int
     cells: torch.Tensor          # (P) int32 output cell of each point, -1 if dropped
-    key_start: torch.Tensor      # (n_keys + 1) int32: key k owns sorted_points[key_start[k]:key_start[k+1]]
-    sorted_points: torch.Tensor  # (P) int32 point ids ordered by (key, point id); first K entries valid
-    sorted_cells: torch.Tensor   # (P) int32 output cell of each sorted point, -1 beyond the K kept points
+    key_start: torch.Tensor      # (n_keys + 1) int32: key k owns sorted_rec[key_start[k]:key_start[k+1]]
+    sorted_rec: torch.Tensor     # (P, 2) int32 {output cell, point id} ordered by (key, point id); {-1, 0} beyond K
     counts: torch.Tensor         # (2) int32 {K, V}
 
     @property
     def P(self) -> int:
         return self.B * self.N * self.D * self.fH * self.fW
+
+    @property
+    def sorted_points(self) -> torch.Tensor:
+        """(P) point ids ordered by (key, point id); the first K entries are valid."""
+        return self.sorted_rec[:, 1]
+
+    @property
+    def sorted_cells(self) -> torch.Tensor:
+        """(P) output cell of each sorted point, -1 beyond the K kept points."""
+        return self.sorted_rec[:, 0]
 
     def shape(self, C: int) -> _abi.LssShape:
         return _abi.make_shape(self.B, self.N, self.D, self.fH, self.fW, C)
@@ -282,17 +303,53 @@ def n_keys(grid: GridSpec, B: int) -> int:
     return int(_abi.load().lss_plan_key_count(grid.c(), B))
 
 
-_WORKSPACES: Dict[Tuple, torch.Tensor] = {}
+class _Workspace:
+    """Scratch of the plan kernels.  Its control part (histogram, per-run counters, tile totals,
+    ticket) must be zero on entry and a successful call leaves it zero again, so a cached
+    workspace is zeroed once; calls on different streams are ordered through an event and a
+    failed call re-zeroes it."""
+
+    def __init__(self, dev, nbytes: int, control: int, cached: bool):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.control = control
+        self.buf[:control].zero_()
+        self.cached = cached
+        if cached:
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(dev))
+            self.stream = _stream(dev)
+
+    def acquire(self, dev) -> torch.Tensor:
+        if self.cached:
+            st = _stream(dev)
+            if st != self.stream:
+                torch.cuda.current_stream(dev).wait_event(self.event)
+                self.stream = st
+        return self.buf
+
+    def release(self, dev) -> None:
+        if self.cached:
+            self.event.record(torch.cuda.current_stream(dev))
+
+    def reset(self) -> None:
+        self.buf[:self.control].zero_()
 
 
-def _workspace(dev, stream: int, nbytes: int) -> torch.Tensor:
-    """Zero-initialised scratch, reused per (device, stream, size)."""
+_WORKSPACES: Dict[Tuple, _Workspace] = {}
+
+
+def _workspace(dev, nbytes: int, control: int) -> _Workspace:
+    """One workspace per (device, size), reused across calls.  While the stream is capturing a CUDA
+    graph a fresh one is taken instead (memory from the graph's pool, zeroed by a captured memset):
+    events and a buffer shared with eager calls have no place inside a graph."""
     if nbytes == 0:
         raise RuntimeError("the plan workspace query rejected the shape/grid")
-    key = (dev.index, stream, nbytes)
+    if torch.cuda.is_current_stream_capturing():
+        return _Workspace(dev, nbytes, control, cached=False)
+    key = (dev.index, nbytes)
     ws = _WORKSPACES.get(key)
     if ws is None:
-        ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        ws = _Workspace(dev, nbytes, control, cached=True)
         _WORKSPACES[key] = ws
     return ws
 
@@ -300,8 +357,7 @@ def _workspace(dev, stream: int, nbytes: int) -> torch.Tensor:
 def _plan_outputs(P: int, nkeys: int, dev):
     return (torch.empty(P, dtype=torch.int32, device=dev),
             torch.empty(nkeys + 1, dtype=torch.int32, device=dev),
-            torch.empty(P, dtype=torch.int32, device=dev),
-            torch.empty(P, dtype=torch.int32, device=dev),
+            torch.empty((P, 2), dtype=torch.int32, device=dev),
             torch.empty(2, dtype=torch.int32, device=dev))
 
 
@@ -313,19 +369,21 @@ def build_plan(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: Gr
     shape = _abi.make_shape(B, N, D, fH, fW, 4)
     g = grid.c()
     P = B * N * D * fH * fW
-    st = _stream(dev)
-    ws = _workspace(dev, st, _abi.load().lss_plan_workspace_bytes(shape, g))
-    cells, key_start, sorted_points, sorted_cells, counts = _plan_outputs(P, n_keys(grid, B), dev)
-    try:
-        _abi.call("lss_build_plan", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
-                  _ptr(_f32c(rots)), _ptr(_f32c(trans)), _ptr(_f32c(intrins)),
-                  _ptr(_f32c(post_rots)), _ptr(_f32c(post_trans)), g, shape, _ptr(cells),
-                  _ptr(key_start), _ptr(sorted_points), _ptr(sorted_cells), _ptr(counts), _ptr(ws),
-                  ws.numel(), st)
-    except _abi.LssError:
-        ws.zero_()  # a failed call may leave the control words dirty
-        raise
-    return Plan(grid, B, N, D, fH, fW, cells, key_start, sorted_points, sorted_cells, counts)
+    lib = _abi.load()
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.lss_plan_workspace_bytes(shape, g), lib.lss_plan_workspace_control_bytes(shape, g))
+        buf = ws.acquire(dev)
+        cells, key_start, sorted_rec, counts = _plan_outputs(P, n_keys(grid, B), dev)
+        try:
+            _abi.call("lss_build_plan", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
+                      _ptr(_f32c(rots)), _ptr(_f32c(trans)), _ptr(_f32c(intrins)),
+                      _ptr(_f32c(post_rots)), _ptr(_f32c(post_trans)), g, shape, _ptr(cells),
+                      _ptr(key_start), _ptr(sorted_rec), _ptr(counts), _ptr(buf), buf.numel(), _stream(dev))
+        except _abi.LssError:
+            ws.reset()  # a failed call may leave the control words dirty
+            raise
+        ws.release(dev)
+    return Plan(grid, B, N, D, fH, fW, cells, key_start, sorted_rec, counts)
 
 
 def plan_from_geom(geom: torch.Tensor, grid: GridSpec) -> Plan:
@@ -336,16 +394,21 @@ def plan_from_geom(geom: torch.Tensor, grid: GridSpec) -> Plan:
     geom = _f32c(geom)
     P = B * N * D * fH * fW
     g = grid.c()
-    st = _stream(dev)
-    ws = _workspace(dev, st, _abi.load().lss_plan_from_geom_workspace_bytes(P, g, B))
-    cells, key_start, sorted_points, sorted_cells, counts = _plan_outputs(P, n_keys(grid, B), dev)
-    try:
-        _abi.call("lss_build_plan_from_geom", _ptr(geom), g, B, P, _ptr(cells), _ptr(key_start),
-                  _ptr(sorted_points), _ptr(sorted_cells), _ptr(counts), _ptr(ws), ws.numel(), st)
-    except _abi.LssError:
-        ws.zero_()
-        raise
-    return Plan(grid, B, N, D, fH, fW, cells, key_start, sorted_points, sorted_cells, counts)
+    shape = _abi.make_shape(B, N, D, fH, fW, 4)
+    lib = _abi.load()
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.lss_plan_from_geom_workspace_bytes(P, g, B),
+                        lib.lss_plan_workspace_control_bytes(shape, g))
+        buf = ws.acquire(dev)
+        cells, key_start, sorted_rec, counts = _plan_outputs(P, n_keys(grid, B), dev)
+        try:
+            _abi.call("lss_build_plan_from_geom", _ptr(geom), g, B, P, _ptr(cells), _ptr(key_start),
+                      _ptr(sorted_rec), _ptr(counts), _ptr(buf), buf.numel(), _stream(dev))
+        except _abi.LssError:
+            ws.reset()
+            raise
+        ws.release(dev)
+    return Plan(grid, B, N, D, fH, fW, cells, key_start, sorted_rec, counts)
 
 
 # --------------------------------------------------------------------------
@@ -369,28 +432,41 @@ def _as_nhwc(grad: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # fused lift + splat (K4 / K5)
 # --------------------------------------------------------------------------
-def lift_stage(depth: torch.Tensor, feat: torch.Tensor, plan: Plan, softmax: bool = False):
-    """Pixel-major float32 staging copies (B*N*fH*fW, D) and (B*N*fH*fW, C).  depth / feat may be
-    float32, float16 or bfloat16 (the AMP scripts hand over half tensors) and channel slices of one
-    conv output; with ``softmax`` the first tensor holds logits and the copy holds softmax over D."""
-    dev = _need_cuda(depth, feat)
-    if depth.dtype != feat.dtype:
-        common = torch.promote_types(depth.dtype, feat.dtype)
-        depth, feat = depth.to(common), feat.to(common)
-    depth, feat = _feature_input(depth), _feature_input(feat)
+def feat_stage(feat: torch.Tensor, plan: Plan) -> torch.Tensor:
+    """Pixel-major float32 copy (B*N*fH*fW, C) of the context features.  feat may be float32, float16
+    or bfloat16 (the AMP scripts hand over half tensors) and a channel slice of a conv output."""
+    dev = _need_cuda(feat)
+    feat = _feature_input(feat)
     BN, C = feat.shape[0], feat.shape[1]
-    HW = plan.fH * plan.fW
-    depth_t = torch.empty((BN * HW, plan.D), dtype=torch.float32, device=dev)
-    feat_t = torch.empty((BN * HW, C), dtype=torch.float32, device=dev)
-    _abi.call("lss_lift_stage_ex", _ptr(depth), depth.stride(0), _ptr(feat), feat.stride(0), plan.shape(C),
-              1 if softmax else 0, _DTYPES[depth.dtype], _ptr(depth_t), _ptr(feat_t), _stream(dev))
-    return depth_t, feat_t
+    feat_t = torch.empty((BN * plan.fH * plan.fW, C), dtype=torch.float32, device=dev)
+    _call(dev, "lss_feat_stage", _ptr(feat), feat.stride(0), plan.shape(C), _DTYPES[feat.dtype], _ptr(feat_t),
+          _stream(dev))
+    return feat_t
+
+
+def depth_softmax(logits: torch.Tensor, plan: Plan) -> torch.Tensor:
+    """softmax over the D logit channels (reference src/modules.py:76-77) -> float32 (B*N, D, fH, fW)."""
+    dev = _need_cuda(logits)
+    logits = _feature_input(logits)
+    BN = logits.shape[0]
+    out = torch.empty((BN, plan.D, plan.fH, plan.fW), dtype=torch.float32, device=dev)
+    _call(dev, "lss_depth_softmax", _ptr(logits), logits.stride(0), plan.shape(4), _DTYPES[logits.dtype], _ptr(out),
+          _stream(dev))
+    return out
+
+
+def _fwd(dev, depth, feat_t, plan: Plan, C: int) -> torch.Tensor:
+    bev = _alloc_bev(plan, C, dev)
+    _call(dev, "lss_liftsplat_fwd", _ptr(depth), depth.stride(0), _DTYPES[depth.dtype], _ptr(feat_t),
+          _ptr(plan.sorted_rec), _ptr(plan.key_start), plan.grid.c(), plan.shape(C), _ptr(bev), _stream(dev))
+    return bev
 
 
 class _LiftSplat(torch.autograd.Function):
     """Counterpart of QuickCumsum (reference src/tools.py:192-218) for the fused op:
-    forward saves the staged inputs and the per-point cell table, index tensors
-    are non-differentiable, backward is one kernel."""
+    forward saves the depth distribution (the caller's tensor, read in place), the staged
+    features and the per-point cell table, index tensors are non-differentiable, backward is
+    one kernel."""
 
     @staticmethod
     def forward(ctx, depth, feat, plan: Plan):
@@ -403,20 +479,21 @@ class _LiftSplat(torch.autograd.Function):
             raise RuntimeError("depth %s / feat %s do not match the plan (B=%d N=%d D=%d fH=%d fW=%d)"
                                % (tuple(depth.shape), tuple(feat.shape), plan.B, plan.N, plan.D,
                                   plan.fH, plan.fW))
-        depth_t, feat_t = lift_stage(depth, feat, plan)
-        bev = _alloc_bev(plan, C, dev)
-        _abi.call("lss_liftsplat_fwd", _ptr(depth_t), _ptr(feat_t), _ptr(plan.sorted_points),
-                  _ptr(plan.sorted_cells), _ptr(plan.key_start), plan.grid.c(), plan.shape(C),
-                  _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
+        ctx.in_dtypes = (depth.dtype, feat.dtype)
+        if depth.dtype != feat.dtype:
+            common = torch.promote_types(depth.dtype, feat.dtype)
+            depth, feat = depth.to(common), feat.to(common)
+        depth_in = _feature_input(depth.detach())          # read in place: indexed by point id
+        feat_t = feat_stage(feat.detach(), plan)
+        bev = _fwd(dev, depth_in, feat_t, plan, C)
         ctx.plan = plan
         ctx.C = C
-        ctx.in_dtypes = (depth.dtype, feat.dtype)
-        ctx.save_for_backward(depth_t, feat_t)
+        ctx.save_for_backward(depth_in, feat_t)
         return bev.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, grad_bev):
-        depth_t, feat_t = ctx.saved_tensors
+        depth, feat_t = ctx.saved_tensors
         plan, C = ctx.plan, ctx.C
         dev = grad_bev.device
         g = _as_nhwc(grad_bev)
@@ -425,9 +502,9 @@ class _LiftSplat(torch.autograd.Function):
         BN, HW = plan.B * plan.N, plan.fH * plan.fW
         ddepth = torch.empty((BN, plan.D, plan.fH, plan.fW), dtype=out_dt, device=dev)
         dfeat = torch.empty((BN, C, plan.fH, plan.fW), dtype=out_dt, device=dev)
-        _abi.call("lss_liftsplat_bwd_ex", _ptr(g), _ptr(depth_t), _ptr(feat_t), _ptr(plan.cells),
-                  plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC, 0, _DTYPES[out_dt], _ptr(ddepth),
-                  plan.D * HW, _ptr(dfeat), C * HW, _stream(dev))
+        _call(dev, "lss_liftsplat_bwd", _ptr(g), _ptr(depth), depth.stride(0), _DTYPES[depth.dtype], _ptr(feat_t),
+              _ptr(plan.cells), plan.grid.c(), plan.shape(C), 0, _DTYPES[out_dt], _ptr(ddepth), plan.D * HW,
+              _ptr(dfeat), C * HW, _stream(dev))
         return ddepth.to(dt_d), dfeat.to(dt_f), None
 
 
@@ -449,10 +526,10 @@ def lift_splat(depth: torch.Tensor, feat: torch.Tensor, plan: Plan,
 
 class _LiftSplatLogits(torch.autograd.Function):
     """lift + splat straight from the CamEncode conv output y = depthnet(x) (reference
-    src/modules.py:82-84): channels [0, D) are the depth LOGITS, [D, D+C) the context features.
-    The softmax of src/modules.py:77, the channel split and the staging transposes are one pass
-    (lss_lift_stage_ex), the softmax backward is fused into K5 (lss_liftsplat_bwd_ex), and the
-    gradient comes back as ONE tensor shaped like y."""
+    src/modules.py:82-84): channels [0, D) are the depth LOGITS, [D, D+C) the context features,
+    both read as channel slices of y (no .contiguous() copies).  The softmax of src/modules.py:77
+    is one small kernel (lss_depth_softmax), its backward is fused into K5 (lss_liftsplat_bwd,
+    softmax=1), and the gradient comes back as ONE tensor shaped like y."""
 
     @staticmethod
     def forward(ctx, y, D: int, C: int, plan: Plan):
@@ -464,32 +541,26 @@ class _LiftSplatLogits(torch.autograd.Function):
             raise RuntimeError("conv output %s does not match D=%d C=%d and the plan (B=%d N=%d D=%d fH=%d fW=%d)"
                                % (tuple(y.shape), D, C, plan.B, plan.N, plan.D, plan.fH, plan.fW))
         ctx.in_dtype = y.dtype
-        yy = _feature_input(y)
-        HW = fH * fW
-        depth_t = torch.empty((BN * HW, D), dtype=torch.float32, device=dev)
-        feat_t = torch.empty((BN * HW, C), dtype=torch.float32, device=dev)
-        _abi.call("lss_lift_stage_ex", yy.data_ptr(), yy.stride(0), yy.data_ptr() + D * HW * yy.element_size(),
-                  yy.stride(0), plan.shape(C), 1, _DTYPES[yy.dtype], _ptr(depth_t), _ptr(feat_t), _stream(dev))
-        bev = _alloc_bev(plan, C, dev)
-        _abi.call("lss_liftsplat_fwd", _ptr(depth_t), _ptr(feat_t), _ptr(plan.sorted_points),
-                  _ptr(plan.sorted_cells), _ptr(plan.key_start), plan.grid.c(), plan.shape(C),
-                  _abi.LSS_BEV_NHWC, _ptr(bev), _stream(dev))
+        yy = _feature_input(y.detach())
+        depth_p = depth_softmax(yy[:, :D], plan)
+        feat_t = feat_stage(yy[:, D:D + C], plan)
+        bev = _fwd(dev, depth_p, feat_t, plan, C)
         ctx.plan, ctx.D, ctx.C, ctx.R = plan, D, C, R
-        ctx.save_for_backward(depth_t, feat_t)
+        ctx.save_for_backward(depth_p, feat_t)
         return bev.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, grad_bev):
-        depth_t, feat_t = ctx.saved_tensors
+        depth_p, feat_t = ctx.saved_tensors
         plan, D, C, R = ctx.plan, ctx.D, ctx.C, ctx.R
         dev = grad_bev.device
         g = _as_nhwc(grad_bev)
         BN, HW = plan.B * plan.N, plan.fH * plan.fW
         out_dt = ctx.in_dtype if ctx.in_dtype in _DTYPES else torch.float32
         dy = (torch.zeros if R > D + C else torch.empty)((BN, R, plan.fH, plan.fW), dtype=out_dt, device=dev)
-        _abi.call("lss_liftsplat_bwd_ex", _ptr(g), _ptr(depth_t), _ptr(feat_t), _ptr(plan.cells),
-                  plan.grid.c(), plan.shape(C), _abi.LSS_BEV_NHWC, 1, _DTYPES[out_dt], dy.data_ptr(), R * HW,
-                  dy.data_ptr() + D * HW * dy.element_size(), R * HW, _stream(dev))
+        _call(dev, "lss_liftsplat_bwd", _ptr(g), _ptr(depth_p), D * HW, _abi.LSS_F32, _ptr(feat_t), _ptr(plan.cells),
+              plan.grid.c(), plan.shape(C), 1, _DTYPES[out_dt], dy.data_ptr(), R * HW,
+              dy.data_ptr() + D * HW * dy.element_size(), R * HW, _stream(dev))
         return dy.to(ctx.in_dtype), None, None, None
 
 
@@ -517,9 +588,8 @@ class _PoolDense(torch.autograd.Function):
         if x2.shape[0] != plan.P:
             raise RuntimeError("x has %d points, plan has %d" % (x2.shape[0], plan.P))
         bev = _alloc_bev(plan, C, dev)
-        _abi.call("lss_pool_dense_fwd", _ptr(x2), _ptr(plan.sorted_points), _ptr(plan.sorted_cells),
-                  _ptr(plan.key_start), plan.grid.c(), plan.B, C, plan.P, _abi.LSS_BEV_NHWC, _ptr(bev),
-                  _stream(dev))
+        _call(dev, "lss_pool_dense_fwd", _ptr(x2), _ptr(plan.sorted_rec), _ptr(plan.key_start), plan.grid.c(),
+              plan.B, C, plan.P, _ptr(bev), _stream(dev))
         ctx.plan = plan
         ctx.x_shape = tuple(x.shape)
         ctx.x_dtype = x.dtype
@@ -531,8 +601,8 @@ class _PoolDense(torch.autograd.Function):
         C = ctx.x_shape[-1]
         g = _as_nhwc(grad_bev)
         dx = torch.empty((plan.P, C), dtype=torch.float32, device=grad_bev.device)
-        _abi.call("lss_pool_dense_bwd", _ptr(g), _ptr(plan.cells), plan.grid.c(), plan.B, C,
-                  plan.P, _abi.LSS_BEV_NHWC, _ptr(dx), _stream(grad_bev.device))
+        _call(grad_bev.device, "lss_pool_dense_bwd", _ptr(g), _ptr(plan.cells), plan.grid.c(), plan.B, C,
+              plan.P, _ptr(dx), _stream(grad_bev.device))
         return dx.view(ctx.x_shape).to(ctx.x_dtype), None
 
 

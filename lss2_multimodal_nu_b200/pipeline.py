@@ -4,7 +4,7 @@ Training and benchmarking call the same shapes every iteration, so everything th
 fixed is fixed once: device buffers, the workspace, and ONE CUDA graph holding the C-ABI call
 sequence of a whole forward + backward of the path
 
-      +-- lss_lift_stage (side stream) --------+
+      +-- lss_feat_stage (side stream) --------+
       |                                        v
   in -+-- lss_build_plan (K0, K1', sort, K3) ----+--> lss_liftsplat_fwd --> lss_liftsplat_bwd
 
@@ -44,6 +44,28 @@ class LiftSplatStep:
             raise RuntimeError("LiftSplatStep runs on CUDA only (no CPU fallback)")
         self.dev, self.grid = dev, grid
         self.B, self.N, self.D, self.fH, self.fW, self.C = B, N, D, fH, fW, C
+        # every buffer below is created (and, where needed, zero-filled) on the step's own stream:
+        # the warm run, the capture and load() all use that stream, so they are ordered behind the fills
+        self._stream = stream if stream is not None else torch.cuda.Stream(dev)
+        self._stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.device(dev), torch.cuda.stream(self._stream):
+            self._allocate(us, vs, ds)
+        self._side = torch.cuda.Stream(dev)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.kernels_per_step = 3 + 1 + 1 + 1      # plan (cells, scan, scatter+order), feature staging, fwd, bwd
+        # warm run outside capture (module load, function attributes), then capture
+        with torch.cuda.device(dev):
+            with torch.cuda.stream(self._stream):
+                self._enqueue(self._stream, self._side)
+            self._stream.synchronize()
+            if capture:
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=self._stream):
+                    self._enqueue(torch.cuda.current_stream(dev), self._side)
+
+    def _allocate(self, us, vs, ds) -> None:
+        dev, grid = self.dev, self.grid
+        B, N, D, fH, fW, C = self.B, self.N, self.D, self.fH, self.fW, self.C
         self.P = B * N * D * fH * fW
         X, Y, Z = grid.nx
         BN, HW = B * N, fH * fW
@@ -74,11 +96,9 @@ class LiftSplatStep:
         self._bev = torch.empty((B, X, Y, Z * C), **f32)
         # plan + staging buffers
         self.cells = torch.empty(self.P, **i32)
-        self.sorted_points = torch.empty(self.P, **i32)
+        self.sorted_rec = torch.empty((self.P, 2), **i32)
         self.key_start = torch.empty(int(_abi.load().lss_plan_key_count(grid.c(), B)) + 1, **i32)
-        self.sorted_cells = torch.empty(self.P, **i32)
         self.counts = torch.zeros(2, **i32)
-        self.depth_t = torch.empty((BN * HW, D), **f32)
         self.feat_t = torch.empty((BN * HW, C), **f32)
         self._shape = _abi.make_shape(B, N, D, fH, fW, C)
         self._g = grid.c()
@@ -86,18 +106,6 @@ class LiftSplatStep:
         if nbytes == 0:
             raise RuntimeError("lss_plan_workspace_bytes rejected the shape/grid")
         self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-        self._stream = stream if stream is not None else torch.cuda.Stream(dev)
-        self._side = torch.cuda.Stream(dev)
-        self._graph: Optional[torch.cuda.CUDAGraph] = None
-        self.kernels_per_step = 4 + 1 + 1 + 1      # plan (cells, scan, scatter, order), stage, fwd, bwd
-        # warm run outside capture (module load, function attributes), then capture
-        with torch.cuda.stream(self._stream):
-            self._enqueue(self._stream, self._side)
-        self._stream.synchronize()
-        if capture:
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph, stream=self._stream):
-                self._enqueue(torch.cuda.current_stream(dev), self._side)
 
     # ---- views ---------------------------------------------------------------------------
     @property
@@ -117,27 +125,28 @@ class LiftSplatStep:
     # ---- the C-ABI call sequence ---------------------------------------------------------
     def enqueue_stage(self, st: int) -> None:
         p = lambda t: t.data_ptr()
-        _abi.call("lss_lift_stage", p(self.inputs["depth"]), p(self.inputs["feat"]), self._shape,
-                  p(self.depth_t), p(self.feat_t), st)
+        _abi.call("lss_feat_stage", p(self.inputs["feat"]), self.C * self.fH * self.fW, self._shape, _abi.LSS_F32,
+                  p(self.feat_t), st)
 
     def enqueue_plan(self, st: int) -> None:
         p = lambda t: t.data_ptr()
         i = self.inputs
         _abi.call("lss_build_plan", p(self.us), p(self.vs), p(self.ds), p(i["rots"]), p(i["trans"]),
                   p(i["intrins"]), p(i["post_rots"]), p(i["post_trans"]), self._g, self._shape,
-                  p(self.cells), p(self.key_start), p(self.sorted_points), p(self.sorted_cells),
-                  p(self.counts), p(self._ws), self._ws.numel(), st)
+                  p(self.cells), p(self.key_start), p(self.sorted_rec), p(self.counts), p(self._ws),
+                  self._ws.numel(), st)
 
     def enqueue_fwd(self, st: int) -> None:
         p = lambda t: t.data_ptr()
-        _abi.call("lss_liftsplat_fwd", p(self.depth_t), p(self.feat_t), p(self.sorted_points),
-                  p(self.sorted_cells), p(self.key_start), self._g, self._shape, _abi.LSS_BEV_NHWC,
-                  p(self._bev), st)
+        _abi.call("lss_liftsplat_fwd", p(self.inputs["depth"]), self.D * self.fH * self.fW, _abi.LSS_F32,
+                  p(self.feat_t), p(self.sorted_rec), p(self.key_start), self._g, self._shape, p(self._bev), st)
 
     def enqueue_bwd(self, st: int) -> None:
         p = lambda t: t.data_ptr()
-        _abi.call("lss_liftsplat_bwd", p(self._dbev), p(self.depth_t), p(self.feat_t), p(self.cells),
-                  self._g, self._shape, _abi.LSS_BEV_NHWC, p(self.ddepth), p(self.dfeat), st)
+        HW = self.fH * self.fW
+        _abi.call("lss_liftsplat_bwd", p(self._dbev), p(self.inputs["depth"]), self.D * HW, _abi.LSS_F32,
+                  p(self.feat_t), p(self.cells), self._g, self._shape, 0, _abi.LSS_F32, p(self.ddepth), self.D * HW,
+                  p(self.dfeat), self.C * HW, st)
 
     def _enqueue(self, main: torch.cuda.Stream, side: torch.cuda.Stream) -> None:
         side.wait_stream(main)                      # fork: staging depends only on the features
@@ -149,7 +158,7 @@ class LiftSplatStep:
 
     def run(self) -> None:
         """Enqueue one forward + backward on ``self.stream`` (graph replay when captured)."""
-        with torch.cuda.stream(self._stream):
+        with torch.cuda.device(self.dev), torch.cuda.stream(self._stream):
             if self._graph is not None:
                 self._graph.replay()
             else:

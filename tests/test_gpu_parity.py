@@ -91,7 +91,7 @@ FIXTURES = ["tiny", "edge_none_kept", "edge_one_voxel", "edge_randn_calib", "edg
 
 def test_library_loaded():
     from lss2_multimodal_nu_b200 import _abi
-    assert _abi.load().lss_abi_version() == _abi.ABI_VERSION == 2
+    assert _abi.load().lss_abi_version() == _abi.ABI_VERSION == 3
 
 
 def test_camera_prep_bit_exact(golden_dir):

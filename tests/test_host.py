@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     loaded = _abi.load()
-    assert loaded.lss_abi_version() == 2
+    assert loaded.lss_abi_version() == _abi.ABI_VERSION == 3
     assert loaded.lss_status_string(-4) == b"workspace too small"
     out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l and "lss_" in l}
