@@ -43,6 +43,7 @@ def parse():
                     help="independent batches in flight (one CUDA stream each); 0: LSS_BENCH_IN_FLIGHT or 4")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="kernel numbers only: no e2e, no cpu baseline (tools/run_variants.sh)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 100)")
     return ap.parse_args()
 
@@ -297,21 +298,32 @@ def run_ours(args, cfg):
     elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
     ms_per_step = elapsed_ms / args.steps
 
-    # ---- per-kernel timing (CUDA events on the launching stream), cold rotating sets ----
-    def time_kernel(name, n):
-        evs = []
+    # ---- per-phase timing: ONE CUDA graph holding the phase's launches for every batch set, back to back on
+    # one stream (rotating sets: cold inputs), replayed between two CUDA events on that stream ----
+    def time_kernel(name, replays):
+        reps = 2
         with torch.cuda.stream(stream):
-            for i in range(n):
-                d = steps[i % len(steps)]
-                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                a.record(stream); getattr(d, "enqueue_" + name)(stream.cuda_stream); b.record(stream)
-                evs.append((a, b))
+            for d in steps:                                    # warm (module load) outside the capture
+                getattr(d, "enqueue_" + name)(stream.cuda_stream)
         stream.synchronize()
-        ts = sorted(a.elapsed_time(b) for a, b in evs)
-        return {"mean_us": 1e3 * sum(ts) / len(ts), "median_us": 1e3 * ts[len(ts) // 2], "min_us": 1e3 * ts[0]}
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            cur = torch.cuda.current_stream(dev).cuda_stream
+            for _ in range(reps):
+                for d in steps:
+                    getattr(d, "enqueue_" + name)(cur)
+        ts = []
+        with torch.cuda.stream(stream):
+            g.replay()
+            for _ in range(replays):
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record(stream); g.replay(); b.record(stream)
+                ts.append((a, b))
+        stream.synchronize()
+        per = sorted(a.elapsed_time(b) * 1e3 / (reps * len(steps)) for a, b in ts)
+        return {"mean_us": sum(per) / len(per), "median_us": per[len(per) // 2], "min_us": per[0]}
 
-    n_k = min(args.steps, 200)
-    kt = {k: time_kernel(k, n_k) for k in ("plan", "stage", "fwd", "bwd")}
+    kt = {k: time_kernel(k, 20) for k in ("plan", "stage", "fwd", "bwd")}
 
     # ---- roofline of the dominant kernel (fused forward) -----------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -338,6 +350,11 @@ def run_ours(args, cfg):
                 "step_frac_of_hbm_roofline": (alg["total"] / (ms_per_step * 1e-3) / 1e9) / peak,
                 "kernels_us": {k: round(v["mean_us"], 2) for k, v in kt.items()}}
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_per_step, "roofline": roofline,
+                              "serial": {"ms_per_step": serial_ms}}))
+        return
     # ---- e2e: HostPipeline (public API), pinned host buffers, two steps in flight ----------
     e2e_steps = args.e2e_steps or min(args.steps, 400)
     pipe = HostPipeline(lambda: LiftSplatStep(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, C, grid, us, vs, ds,

@@ -72,45 +72,59 @@ static int run_plan(const GeomArgs* ga, const float* dense_geom, const GridDev& 
   LSS_REQUIRE(aligned16(ws) && aligned16(d_key_start) && aligned16(d_sorted_rec), LSS_ERR_MISALIGNED);
   char* w = static_cast<char*>(ws);
   uint32_t* cnt = reinterpret_cast<uint32_t*>(w + pw.off_cnt);
-  uint32_t* done = reinterpret_cast<uint32_t*>(w + pw.off_done);
   uint32_t* tsum = reinterpret_cast<uint32_t*>(w + pw.off_tsum);
-  uint32_t* ctl = reinterpret_cast<uint32_t*>(w + pw.off_ctl);
   int32_t* keys = reinterpret_cast<int32_t*>(w + pw.off_keys);
-  int32_t* tmp = reinterpret_cast<int32_t*>(w + pw.off_tmp);
-  int32_t* long_list = reinterpret_cast<int32_t*>(w + pw.off_long);
+  int2* tmp = reinterpret_cast<int2*>(w + pw.off_tmp);
 
   PlanCellsArgs ca;
   memset(&ca, 0, sizeof(ca));
   ca.grid = g; ca.keys = km; ca.P = P; ca.cells = d_cells; ca.key_of_point = keys; ca.cnt = cnt; ca.tsum = tsum;
-  ca.tile_shift = pw.tile_shift; ca.counts = d_counts; ca.ctl = ctl;
-  const unsigned tiles = (unsigned)((P + kPlanTile - 1) / kPlanTile);
+  ca.tile_shift = pw.tile_shift; ca.scan_tiles = pw.scan_tiles; ca.counts = d_counts;
   if (ga) {
     ca.geom = *ga;
     const int hw = ga->fH * ga->fW;
-    LSS_REQUIRE((kPlanTile - 1) / (ga->D * hw) + 2 <= kPlanMaxCams, LSS_ERR_UNSUPPORTED);
-    ca.div_ppc = FastDiv((uint32_t)(ga->D * hw)); ca.div_hw = FastDiv((uint32_t)hw);
     ca.div_w = FastDiv((uint32_t)ga->fW); ca.div_n = FastDiv((uint32_t)ga->N);
-    plan_cells_kernel<false><<<tiles, kPlanThreads, 0, st>>>(ca);
+    // CTA = as many pixels of one camera as fit 256 threads evenly, kPlanDepths depth bins each
+    const int px_blocks = (hw + kPlanThreads - 1) / kPlanThreads;
+    int threads = ((hw + px_blocks - 1) / px_blocks + 31) / 32 * 32;
+    const long long bn = P / ((long long)ga->D * hw);
+    LSS_REQUIRE(bn <= 65535 && (ga->D + kPlanDepths - 1) / kPlanDepths <= 65535, LSS_ERR_BAD_DIMENSION);
+    dim3 grid(px_blocks, (ga->D + kPlanDepths - 1) / kPlanDepths, (unsigned)bn);
+    LSS_CUDA_TRY(launch_chain(kPdlPlan, plan_cells_kernel, grid, dim3(threads), 0, st, ca), "plan_cells_kernel");
   } else {
     ca.dense_geom = dense_geom;
     ca.div_pps = FastDiv((uint32_t)points_per_sample);
-    plan_cells_kernel<true><<<tiles, kPlanThreads, 0, st>>>(ca);
+    LSS_CUDA_TRY(launch_chain(kPdlPlan, plan_cells_dense_kernel, dim3((unsigned)((P + kPlanThreads - 1) / kPlanThreads)), dim3(kPlanThreads), 0, st, ca), "plan_cells_dense_kernel");
   }
   LSS_LAUNCH_CHECK("plan_cells_kernel");
+#if defined(LSS_DBG_PLAN_UPTO) && LSS_DBG_PLAN_UPTO < 2
+  return LSS_OK;
+#endif
 
   PlanScanArgs sa;
   sa.cnt = cnt; sa.tsum = tsum; sa.n = km.n_keys; sa.tiles = pw.scan_tiles; sa.tile_shift = pw.tile_shift;
   sa.key_start = d_key_start; sa.counts = d_counts;
-  plan_scan_kernel<<<(unsigned)pw.scan_tiles, kPlanThreads, 0, st>>>(sa);
+  LSS_CUDA_TRY(launch_chain(kPdlPlan, plan_scan_kernel, dim3((unsigned)pw.scan_tiles), dim3(kPlanThreads), 0, st, sa), "plan_scan_kernel");
   LSS_LAUNCH_CHECK("plan_scan_kernel");
+#if defined(LSS_DBG_PLAN_UPTO) && LSS_DBG_PLAN_UPTO < 3
+  return LSS_OK;
+#endif
 
   PlanScatterArgs sc;
-  sc.key_of_point = keys; sc.cells = d_cells; sc.P = P; sc.cnt = cnt; sc.done = done; sc.key_start = d_key_start;
-  sc.n_keys = km.n_keys; sc.tmp = tmp; sc.rec = reinterpret_cast<int2*>(d_sorted_rec); sc.tsum = tsum;
-  sc.scan_tiles = pw.scan_tiles; sc.ctl = ctl; sc.long_list = long_list; sc.keys = km;
+  sc.key_of_point = keys; sc.cells = d_cells; sc.P = P; sc.cnt = cnt; sc.key_start = d_key_start;
+  sc.tmp = tmp; sc.tsum = tsum; sc.scan_tiles = pw.scan_tiles;
   const long long blocks = (P + kPlanThreads - 1) / kPlanThreads;
-  plan_scatter_kernel<<<(unsigned)blocks, kPlanThreads, 0, st>>>(sc);
+  LSS_CUDA_TRY(launch_chain(kPdlPlan, plan_scatter_kernel, dim3((unsigned)blocks), dim3(kPlanThreads), 0, st, sc), "plan_scatter_kernel");
   LSS_LAUNCH_CHECK("plan_scatter_kernel");
+#if defined(LSS_DBG_PLAN_UPTO) && LSS_DBG_PLAN_UPTO < 4
+  return LSS_OK;
+#endif
+
+  PlanOrderArgs oa;
+  oa.tmp = tmp; oa.key_start = d_key_start; oa.n_keys = km.n_keys; oa.P = P;
+  oa.rec = reinterpret_cast<int2*>(d_sorted_rec); oa.keys = km;
+  LSS_CUDA_TRY(launch_chain(kPdlPlan, plan_order_kernel, dim3((unsigned)blocks), dim3(kPlanThreads), 0, st, oa), "plan_order_kernel");
+  LSS_LAUNCH_CHECK("plan_order_kernel");
   return LSS_OK;
 }
 
@@ -135,7 +149,7 @@ static int launch_pool_fwd(const PoolFwdArgs& a0, int blocks, cudaStream_t st) {
   a.nact = l.nact;
 #define LSS_FWD_CASE(LL, NP, T2)                                                                  \
   if (l.L == LL && l.np == NP && l.t2 == T2) {                                                     \
-    pool_fwd_kernel<kFused, LL, NP, (T2 != 0), LSS_FWD_M><<<blocks, kPoolThreads, 0, st>>>(a);     \
+    LSS_CUDA_TRY(launch_chain(kPdlFwd, pool_fwd_kernel<kFused, LL, NP, (T2 != 0), LSS_FWD_M>, dim3(blocks), dim3(kPoolThreads), 0, st, a), "pool_fwd_kernel"); \
     LSS_LAUNCH_CHECK("pool_fwd_kernel");                                                           \
     return LSS_OK;                                                                                 \
   }
@@ -146,30 +160,41 @@ static int launch_pool_fwd(const PoolFwdArgs& a0, int blocks, cudaStream_t st) {
   return LSS_ERR_UNSUPPORTED;
 }
 
+#ifndef LSS_BWD_WIDE
+#define LSS_BWD_WIDE 1      // 1: C = 64 / 128 use 16-lane walkers (fewer registers, more warps in flight)
+#endif
+#ifndef LSS_BWD_BINS
+#define LSS_BWD_BINS 20     // depth bins a warp should at least own (slices of D)
+#endif
+
 static int launch_bwd(const PoolBwdArgs& a0, cudaStream_t st) {
   PoolBwdArgs a = a0;
-  const LaneLayout l = lane_layout(a.C, 8);
+  LaneLayout l = lane_layout(a.C, 8);
+  if (LSS_BWD_WIDE && l.t2 == 0 && l.L == 8 && (l.np == 2 || l.np == 4)) { l.L = 16; l.np /= 2; l.nact = 16; }
   a.nact = l.nact;
   const int G = 32 / l.L;
   int rgw = 1;
-  while (rgw < 8 && rgw * G < a.fH) rgw <<= 1;
+  while (rgw < kBwdMaxWarps && rgw * G < a.fH) rgw <<= 1;
   a.rg_warps = rgw;
-  const int slices = kBwdWarps / rgw;
+  int slices = kBwdMaxWarps / rgw;
+  while (slices > 1 && (a.D + slices - 1) / slices < LSS_BWD_BINS) slices >>= 1;
+  a.slices = slices;
   a.d_per_slice = (a.D + slices - 1) / slices;
   a.row_blocks = (a.fH + rgw * G - 1) / (rgw * G);
   const long long blocks = (long long)a.BN * a.fW * a.row_blocks;
+  const int threads = 32 * rgw * slices;
   LSS_REQUIRE(blocks < (1ll << 31), LSS_ERR_BAD_DIMENSION);
   const bool general = a.softmax || a.out_dtype != LSS_F32;
 #define LSS_BWD_CASE(LL, NP, T2)                                                                  \
   if (l.L == LL && l.np == NP && l.t2 == T2) {                                                     \
-    if (general) liftsplat_bwd_kernel<LL, NP, (T2 != 0), true><<<(unsigned)blocks, kBwdThreads, 0, st>>>(a);  \
-    else liftsplat_bwd_kernel<LL, NP, (T2 != 0), false><<<(unsigned)blocks, kBwdThreads, 0, st>>>(a);         \
+    if (general) LSS_CUDA_TRY(launch_chain(kPdlBwd, liftsplat_bwd_kernel<LL, NP, (T2 != 0), true>, dim3((unsigned)blocks), dim3(threads), 0, st, a), "liftsplat_bwd_kernel");  \
+    else LSS_CUDA_TRY(launch_chain(kPdlBwd, liftsplat_bwd_kernel<LL, NP, (T2 != 0), false>, dim3((unsigned)blocks), dim3(threads), 0, st, a), "liftsplat_bwd_kernel");         \
     LSS_LAUNCH_CHECK("liftsplat_bwd_kernel");                                                      \
     return LSS_OK;                                                                                 \
   }
   LSS_BWD_CASE(8, 1, 0) LSS_BWD_CASE(8, 2, 0) LSS_BWD_CASE(8, 3, 0) LSS_BWD_CASE(8, 4, 0)
   LSS_BWD_CASE(8, 1, 1) LSS_BWD_CASE(8, 2, 1) LSS_BWD_CASE(8, 3, 1)
-  LSS_BWD_CASE(16, 1, 0) LSS_BWD_CASE(32, 1, 0)
+  LSS_BWD_CASE(16, 1, 0) LSS_BWD_CASE(16, 2, 0) LSS_BWD_CASE(32, 1, 0)
 #undef LSS_BWD_CASE
   return LSS_ERR_UNSUPPORTED;
 }
@@ -364,7 +389,7 @@ int lss_feat_stage(const void* d_feat, int64_t feat_batch_stride, const LssShape
   LSS_REQUIRE(feat_batch_stride >= (long long)C * HW, LSS_ERR_BAD_DIMENSION);
   const int vec_ok = (dtype == LSS_F32 && HW % 4 == 0 && feat_batch_stride % 4 == 0 && aligned16(d_feat)) ? 1 : 0;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, BN);
-  feat_stage_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_feat, feat_batch_stride, dtype, vec_ok, C, HW, d_feat_t);
+  LSS_CUDA_TRY(launch_chain(kPdlStage, feat_stage_kernel, grid, dim3(256), 0, as_stream(stream), d_feat, (long long)feat_batch_stride, (int)dtype, vec_ok, C, HW, d_feat_t), "feat_stage_kernel");
   LSS_LAUNCH_CHECK("feat_stage_kernel");
   return LSS_OK;
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -82,6 +83,7 @@ struct FastDiv {
 struct GridDev {
   float off[3];  // bx - dx/2   (reference src/model_baseline.py:92)
   float dx[3];
+  float rdx[3];  // 1/dx where dx is a power of two (then x / dx == x * rdx bit for bit), else 0
   float nxf[3];
   int32_t nx[3];
   int32_t B;
@@ -100,6 +102,11 @@ inline int make_grid(const LssGrid* g, int32_t B, GridDev* out) {
     volatile float off = g->bx[i] - half;
     out->off[i] = off;
     out->dx[i] = g->dx[i];
+    {
+      int e = 0;
+      const float m = frexpf(g->dx[i], &e);
+      out->rdx[i] = (m == 0.5f && e > -120 && e < 120) ? ldexpf(1.0f, 1 - e) : 0.0f;
+    }
     out->nx[i] = g->nx[i];
     out->nxf[i] = static_cast<float>(g->nx[i]);
   }
@@ -171,6 +178,41 @@ inline bool valid_dtype(int d) { return d == LSS_F32 || d == LSS_F16 || d == LSS
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// ---- programmatic dependent launch (build with -DLSS_PDL=1) -------------------------------------
+// The kernels of one step form a chain on one stream.  Launched with the programmatic-serialization
+// attribute, a kernel may be SCHEDULED while its predecessor still runs; pdl_wait() then holds it until
+// the predecessor has completed and its writes are visible, so what overlaps is launch latency, block
+// scheduling and the prologue before the wait.  Every kernel of the chain calls pdl_wait() before its
+// first global-memory access (reads and writes: the predecessor may still be reading what this kernel
+// overwrites) and pdl_trigger() right after, which lets ITS successor be scheduled once all of its own
+// blocks have started.  Without the attribute both are no-ops.
+#ifndef LSS_PDL
+#define LSS_PDL 0
+#endif
+__device__ __forceinline__ void pdl_wait() {
+#if LSS_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// LSS_PDL is a bit mask of the kernels launched as programmatic dependents
+constexpr int kPdlPlan = 1, kPdlFwd = 2, kPdlBwd = 4, kPdlStage = 8;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (LSS_PDL & which) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // Optional phase timestamps (build with -DLSS_PHASE_TIMING; tools/phase_timing.py reads them).
 #ifdef LSS_PHASE_TIMING
 __device__ unsigned long long g_phase_ts[3][4096 * 16];
@@ -192,61 +234,5 @@ __device__ __forceinline__ void phase_stamp(int kernel, int slot) {
 __device__ __forceinline__ void phase_stamp_any(int, int) {}
 __device__ __forceinline__ void phase_stamp(int, int) {}
 #endif
-
-__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
-
-// 128-bit read-only load that the compiler may not sink towards its first use: a batch of these
-// stays a batch, i.e. all of them are in flight before the first result is consumed.
-__device__ __forceinline__ float4 ldg_f4_issue(const float4* p, bool pred) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "l"(p), "r"(static_cast<int>(pred)));
-  return v;
-}
-
-// L2 residency control.  The forward streams 82 MB of BEV through a 126 MB L2 while it keeps
-// re-reading ~9 MB of small tables (staged features, sorted points, intervals): the stream is
-// marked evict-first and the tables evict-last, so the tables stay resident instead of being
-// pushed out to HBM (where their reloads would queue behind the write-back traffic).
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void st_f4_hint(float4* p, float4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
-               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
-}
-// streaming 128-bit store (no hint)
-__device__ __forceinline__ void st_stream_f4(float4* p, float4 v) { __stcs(p, v); }
-
-// predicated 128-bit read-only load with an L2 policy; like ldg_f4_issue it is not sunk
-__device__ __forceinline__ float4 ldg_f4_issue_hint(const float4* p, bool pred, uint64_t pol) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-      "@q ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %6;\n\t}"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "l"(p), "r"(static_cast<int>(pred)), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ int32_t ldg_i32_hint(const int32_t* p, uint64_t pol) {
-  int32_t v;
-  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ float ldg_f32_hint(const float* p, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-  return v;
-}
 
 }  // namespace lss

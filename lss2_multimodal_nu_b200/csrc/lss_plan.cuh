@@ -5,7 +5,7 @@
 //
 // The voxel rank has few distinct values (n_cells = B*X*Y*Z, 320 k at the
 // headline config, about one point per cell), so the sort is a ONE-DIGIT radix
-// sort whose digit is the whole key -- a counting sort -- in three small kernels:
+// sort whose digit is the whole key -- a counting sort -- in four small kernels:
 //   P1 cells    camera preparation (K0) + frustum geometry (K1') per point ->
 //               output cell and key; one RED.ADD per kept point builds the key
 //               histogram, one warp-aggregated RED.ADD per warp and scan tile the
@@ -16,11 +16,13 @@
 //               key_start[k] .. key_start[k+1] is key k's run in the sorted
 //               order: the interval table (K3) IS the scanned histogram
 //   P3 scatter  every kept point takes a slot of its key's run (atomic cursor =
-//               the histogram counted back to zero) and the LAST point to arrive
-//               in a run puts the run in ascending point order, which is the
-//               order a STABLE sort gives (argsort on torch's radix path): runs
-//               of <= 8 points in registers, <= 256 with its warp, longer ones
-//               (adversarial inputs) by the last CTA of the grid (bitonic).
+//               the histogram counted back to zero) and parks {cell, id} there
+//   P4 order    the slots of a run are put in ascending point order, which is the
+//               order a STABLE sort gives (argsort on torch's radix path): a
+//               slot finds its run by looking at its neighbours (equal cell) and
+//               counts the smaller ids -- no key arithmetic, no table lookups.
+//               Runs of more than 64 points (coarse grids, adversarial inputs) are
+//               ordered by the warp that holds their first slot.
 // The key is the OUTPUT CELL in tile-major order (KeyMap, lss_common.cuh): the
 // digits (b, x, y, z) of the reference's rank x*(Y*Z*B) + y*(Z*B) + z*B + b
 // regrouped as (b, x/8, y/8, x%8, y%8, z) -- a bijection of the rank, so runs,
@@ -37,16 +39,14 @@
 namespace lss {
 
 constexpr int kPlanThreads = 256;
-constexpr int kPlanItems = 4;
-constexpr int kPlanTile = kPlanThreads * kPlanItems;   // points per CTA in P1
-constexpr int kPlanMaxCams = 24;                       // cameras one P1 tile may span
 constexpr int kScanBlock = kPlanThreads * 4;           // keys per scan step (one uint4 per thread)
 constexpr int kScanMaxTiles = 1024;                    // tile totals a scan CTA sums for its base
-constexpr int kRunSerial = 8;                          // runs up to this: ordered by one thread, in registers
-constexpr int kRunWarp = 256;                          // ... up to this: by the finisher's warp; longer: last CTA
+constexpr int kTsumCopies = 8;                         // replicas of the tile totals (spreads the atomics of P1)
+constexpr int kRunSerial = 64;                         // runs up to this: every slot counts the smaller ids of its run
+constexpr int kRunWarp = 256;                          // ... up to this: by the warp of the run's first slot; longer: last CTA
 
 struct PlanWorkspace {
-  size_t off_cnt, off_done, off_tsum, off_ctl, off_keys, off_tmp, off_long, control_bytes, total_bytes;
+  size_t off_cnt, off_tsum, off_ctl, off_keys, off_tmp, control_bytes, total_bytes;
   int tile_shift;   // a scan tile holds 1 << tile_shift keys
   int scan_tiles;
 };
@@ -60,134 +60,170 @@ inline PlanWorkspace make_plan_workspace(long long P, int32_t n_keys) {
   size_t off = 0;
   // control part: zero on entry, left zero by a successful call
   w.off_cnt = off; off += align_up((size_t)n_keys * 4, 256);
-  w.off_done = off; off += align_up((size_t)n_keys * 4, 256);
-  w.off_tsum = off; off += align_up((size_t)w.scan_tiles * 4, 256);
-  w.off_ctl = off; off += 256;                        // [0] CTA ticket of P3, [1] number of long runs
+  w.off_tsum = off; off += align_up((size_t)w.scan_tiles * kTsumCopies * 4, 256);
+  w.off_ctl = off; off += 256;                        // spare control words
   w.control_bytes = off;
   w.off_keys = off; off += align_up((size_t)P * 4, 256);
-  w.off_tmp = off; off += align_up((size_t)P * 4, 256);
-  w.off_long = off; off += align_up((size_t)(P / kRunWarp + 2) * 4, 256);
+  w.off_tmp = off; off += align_up((size_t)P * 8, 256);   // {cell, id} in arrival order
   w.total_bytes = off;
   return w;
 }
 
 // ---------------------------------------------------------------------------
 // P1: per point output cell (-1: dropped) and sort key, histogram of the keys,
-// totals per scan tile.
-// kDense: the ego-frame points come from a materialised geometry tensor (the
-// literal voxel_pooling(geom_feats, x) call) instead of the calibration.
+// totals per scan tile.  Two variants: from the calibration (plan_cells_kernel)
+// and from a materialised geometry tensor, the literal voxel_pooling(geom_feats, x)
+// call (plan_cells_dense_kernel).
 // ---------------------------------------------------------------------------
 struct PlanCellsArgs {
   GeomArgs geom;            // raw calibration + frustum axes (fused variant)
   const float* dense_geom;  // (P,3) (dense variant)
   GridDev grid;
   KeyMap keys;
-  FastDiv div_ppc, div_hw, div_w, div_n, div_pps;
+  FastDiv div_w, div_n, div_pps;
   long long P;
   int32_t* cells;           // (P)
   int32_t* key_of_point;    // (P) workspace
   uint32_t* cnt;            // (n_keys) zero on entry
-  uint32_t* tsum;           // (scan_tiles) zero on entry
+  uint32_t* tsum;           // (kTsumCopies, scan_tiles) zero on entry
   int tile_shift;
+  int scan_tiles;
   int32_t* counts;          // {K, V}: cleared here
-  uint32_t* ctl;            // ctl[1] = n_long: cleared here
 };
 
-template <bool kDense>
+// quantise (reference src/model_baseline.py:92, 99-101: same float32 operations as
+// quantize_point_core; a division by a power of two is done as the bit-identical multiplication),
+// cell, key, histogram, tile totals.  Every lane of the warp must call it (`in` = has a point).
+static_assert(kKeyTile == 8, "the key arithmetic below shifts by 3");
+__device__ __forceinline__ void plan_emit_point(float gx, float gy, float gz, int b, long long p, bool in,
+                                                const PlanCellsArgs& a, int lane, int copy) {
+  uint32_t tile = 0xffffffffu;                       // dropped / no point: no tile
+  if (in) {
+    const GridDev& g = a.grid;
+    const float sx = __fsub_rn(gx, g.off[0]), sy = __fsub_rn(gy, g.off[1]), sz = __fsub_rn(gz, g.off[2]);
+    const float qx = g.rdx[0] != 0.f ? __fmul_rn(sx, g.rdx[0]) : __fdiv_rn(sx, g.dx[0]);
+    const float qy = g.rdx[1] != 0.f ? __fmul_rn(sy, g.rdx[1]) : __fdiv_rn(sy, g.dx[1]);
+    const float qz = g.rdx[2] != 0.f ? __fmul_rn(sz, g.rdx[2]) : __fdiv_rn(sz, g.dx[2]);
+    // .long() truncates toward zero, so (-1, 0) lands in voxel 0 and is KEPT; NaN / inf fail
+    const bool keep = (qx > -1.0f) && (qx < g.nxf[0]) && (qy > -1.0f) && (qy < g.nxf[1]) &&
+                      (qz > -1.0f) && (qz < g.nxf[2]);
+    int32_t cell = -1, key = -1;
+    if (keep) {
+      const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
+      cell = ((b * g.nx[0] + ix) * g.nx[1] + iy) * g.nx[2] + iz;
+      key = ((((b * a.keys.XT + (ix >> 3)) * a.keys.YT + (iy >> 3)) * 8 + (ix & 7)) * 8 + (iy & 7)) * g.nx[2] + iz;
+#ifndef LSS_DBG_P1_NOATOM
+      atomicAdd(a.cnt + key, 1u);                    // result unused: RED.ADD
+#endif
+      tile = static_cast<uint32_t>(key) >> a.tile_shift;
+    }
+    a.cells[p] = cell;
+    a.key_of_point[p] = key;
+  }
+  // tile totals: the lanes of a warp are neighbours in the image, i.e. on the map, so they fall
+  // into one or two scan tiles -- one RED.ADD per distinct tile, spread over kTsumCopies replicas of
+  // the totals (a few hundred addresses take every warp's adds: one copy serialises in L2)
+#ifndef LSS_DBG_P1_NOTSUM
+  const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+  if (tile != 0xffffffffu && (__ffs(peers) - 1) == lane)
+    atomicAdd(a.tsum + copy * a.scan_tiles + tile, static_cast<uint32_t>(__popc(peers)));
+#endif
+}
+
+// dense variant: the ego-frame points come from a materialised geometry tensor
+__global__ void __launch_bounds__(kPlanThreads)
+plan_cells_dense_kernel(PlanCellsArgs a) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.counts[0] = 0; a.counts[1] = 0; }
+  const long long p = (long long)blockIdx.x * kPlanThreads + threadIdx.x;
+  const bool in = p < a.P;
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  int b = 0;
+  if (in) {
+    gx = __ldg(a.dense_geom + p * 3 + 0);
+    gy = __ldg(a.dense_geom + p * 3 + 1);
+    gz = __ldg(a.dense_geom + p * 3 + 2);
+    b = static_cast<int>(a.div_pps.div(static_cast<uint32_t>(p)));
+  }
+  plan_emit_point(gx, gy, gz, b, p, in, a, lane, static_cast<int>((blockIdx.x * 8 + (threadIdx.x >> 5)) % kTsumCopies));
+}
+
+// fused variant: grid = (pixel blocks, depth chunks, cameras).  A thread owns one pixel (h, w) of
+// one camera and walks kPlanDepths depth bins: everything that does not depend on the depth --
+// the camera's matrices, the pixel's (u, v) and the first two products of every row of
+// inverse(post_rots) @ p -- is computed once.  Operation order and rounding are those of
+// geometry_rank_kernel (reference src/model_baseline.py:59-68): (m0*p0 + m1*p1) + m2*p2, no FMA.
+#ifndef LSS_PLAN_DEPTHS
+#define LSS_PLAN_DEPTHS 8
+#endif
+constexpr int kPlanDepths = LSS_PLAN_DEPTHS;
+
 __global__ void __launch_bounds__(kPlanThreads)
 plan_cells_kernel(PlanCellsArgs a) {
-  __shared__ float s_cam[kDense ? 1 : kPlanMaxCams * 24];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long tile_base = (long long)blockIdx.x * kPlanTile;
-  const long long warp_base = tile_base + (long long)warp * (32 * kPlanItems);
-  if (blockIdx.x == 0 && tid == 0) {
-    a.counts[0] = 0; a.counts[1] = 0;
-    a.ctl[1] = 0u;
+  __shared__ float s_cam[24];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int bn = blockIdx.z;
+  pdl_wait();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && bn == 0 && tid == 0) { a.counts[0] = 0; a.counts[1] = 0; }
+  const int second = blockDim.x >= 64 ? 32 : 1;          // the two inversions run in different warps when there are two
+#ifdef LSS_DBG_P1_NOPREP
+  if (tid < 24) s_cam[tid] = a.geom.rots[bn * 9 + (tid % 9)];
+  if (false) {
+#else
+  if (tid == 0) {
+#endif
+    float pr[9], ipr[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) pr[j] = a.geom.post_rots[bn * 9 + j];
+    inverse3x3(pr, ipr);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) s_cam[j] = ipr[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s_cam[18 + j] = a.geom.post_trans[bn * 3 + j];
+  } else if (tid == second) {
+    float r[9], k[9], ii[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { r[j] = a.geom.rots[bn * 9 + j]; k[j] = a.geom.intrins[bn * 9 + j]; }
+    inverse3x3(k, ii);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        s_cam[9 + i * 3 + j] = dot3_nofma(r[i * 3 + 0], r[i * 3 + 1], r[i * 3 + 2], ii[0 + j], ii[3 + j], ii[6 + j]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s_cam[21 + j] = a.geom.trans[bn * 3 + j];
   }
-  int bn0 = 0;
-  if (!kDense) {
-    long long last = tile_base + kPlanTile - 1;
-    if (last >= a.P) last = a.P - 1;
-    bn0 = static_cast<int>(a.div_ppc.div(static_cast<uint32_t>(tile_base)));
-    const int bn1 = static_cast<int>(a.div_ppc.div(static_cast<uint32_t>(last)));
-    // two threads per camera touched by this tile (host: <= kPlanMaxCams): warp 0 inverts
-    // post_rots, warp 1 inverts intrins and forms rots @ inverse(intrins)
-    const int ncam = bn1 - bn0 + 1;
-    if (warp < 2 && lane < ncam) {
-      const int bn = bn0 + lane;
-      float* c = s_cam + lane * 24;
-      if (warp == 0) {
-        float pr[9], ipr[9];
+  __syncthreads();
+  const int HW = a.geom.fH * a.geom.fW;
+  const int hw = blockIdx.x * blockDim.x + tid;
+  const bool in = hw < HW;
+  uint32_t h, w;
+  a.div_w.divmod(static_cast<uint32_t>(in ? hw : 0), h, w);
+  float c[24];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) pr[j] = a.geom.post_rots[bn * 9 + j];
-        inverse3x3(pr, ipr);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) c[j] = ipr[j];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) c[18 + j] = a.geom.post_trans[bn * 3 + j];
-      } else {
-        float r[9], k[9], ii[9];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) { r[j] = a.geom.rots[bn * 9 + j]; k[j] = a.geom.intrins[bn * 9 + j]; }
-        inverse3x3(k, ii);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j)
-            c[9 + i * 3 + j] = dot3_nofma(r[i * 3 + 0], r[i * 3 + 1], r[i * 3 + 2], ii[0 + j], ii[3 + j], ii[6 + j]);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) c[21 + j] = a.geom.trans[bn * 3 + j];
-      }
-    }
-    __syncthreads();
-  }
-  PointOut out{nullptr, nullptr, nullptr, a.cells};
-#pragma unroll
-  for (int j = 0; j < kPlanItems; ++j) {
-    const long long p = warp_base + j * 32 + lane;
-    const bool in = p < a.P;
-    uint32_t tile = 0xffffffffu;                     // dropped / out of range: no tile
-    if (in) {
-      float gx, gy, gz;
-      int b;
-      if (kDense) {
-        gx = __ldg(a.dense_geom + p * 3 + 0);
-        gy = __ldg(a.dense_geom + p * 3 + 1);
-        gz = __ldg(a.dense_geom + p * 3 + 2);
-        b = static_cast<int>(a.div_pps.div(static_cast<uint32_t>(p)));
-      } else {
-        uint32_t bn, i, d, rem, h, w;
-        a.div_ppc.divmod(static_cast<uint32_t>(p), bn, i);
-        a.div_hw.divmod(i, d, rem);
-        a.div_w.divmod(rem, h, w);
-        const float* c = s_cam + (static_cast<int>(bn) - bn0) * 24;
-        // identical operation order to geometry_rank_kernel (reference model_baseline.py:59-68)
-        const float p0 = __fsub_rn(__ldg(a.geom.us + w), c[18]);
-        const float p1 = __fsub_rn(__ldg(a.geom.vs + h), c[19]);
-        const float p2 = __fsub_rn(__ldg(a.geom.ds + d), c[20]);
-        const float q0 = dot3_nofma(c[0], c[1], c[2], p0, p1, p2);
-        const float q1 = dot3_nofma(c[3], c[4], c[5], p0, p1, p2);
-        const float q2 = dot3_nofma(c[6], c[7], c[8], p0, p1, p2);
-        const float r0 = __fmul_rn(q0, q2), r1 = __fmul_rn(q1, q2), r2 = q2;
-        gx = __fadd_rn(dot3_nofma(c[9], c[10], c[11], r0, r1, r2), c[21]);
-        gy = __fadd_rn(dot3_nofma(c[12], c[13], c[14], r0, r1, r2), c[22]);
-        gz = __fadd_rn(dot3_nofma(c[15], c[16], c[17], r0, r1, r2), c[23]);
-        b = static_cast<int>(a.div_n.div(bn));
-      }
-      int32_t cell;
-      quantize_point_core(gx, gy, gz, b, a.grid, p, out, &cell);
-      int32_t key = -1;
-      if (cell >= 0) {
-        key = static_cast<int32_t>(a.keys.key_of_cell(static_cast<uint32_t>(cell)));
-        atomicAdd(a.cnt + key, 1u);                  // result unused: RED.ADD
-        tile = static_cast<uint32_t>(key) >> a.tile_shift;
-      }
-      a.key_of_point[p] = key;
-    }
-    // tile totals: the lanes of a warp are neighbours in the image, i.e. on the map, so they fall
-    // into one or two scan tiles -- one RED.ADD per distinct tile
-    const uint32_t peers = __match_any_sync(0xffffffffu, tile);
-    if (tile != 0xffffffffu && (__ffs(peers) - 1) == lane) atomicAdd(a.tsum + tile, static_cast<uint32_t>(__popc(peers)));
+  for (int j = 0; j < 24; ++j) c[j] = s_cam[j];
+  const float p0 = __fsub_rn(__ldg(a.geom.us + w), c[18]);
+  const float p1 = __fsub_rn(__ldg(a.geom.vs + h), c[19]);
+  const float a0 = __fadd_rn(__fmul_rn(c[0], p0), __fmul_rn(c[1], p1));
+  const float a1 = __fadd_rn(__fmul_rn(c[3], p0), __fmul_rn(c[4], p1));
+  const float a2 = __fadd_rn(__fmul_rn(c[6], p0), __fmul_rn(c[7], p1));
+  const int b = static_cast<int>(a.div_n.div(static_cast<uint32_t>(bn)));
+  const int copy = static_cast<int>((blockIdx.x + blockIdx.y + blockIdx.z + (tid >> 5)) % kTsumCopies);
+  const int d0 = blockIdx.y * kPlanDepths;
+  const int d1 = min(a.geom.D, d0 + kPlanDepths);
+  long long p = ((long long)bn * a.geom.D + d0) * HW + hw;
+#pragma unroll 4
+  for (int d = d0; d < d1; ++d, p += HW) {
+    const float p2 = __fsub_rn(__ldg(a.geom.ds + d), c[20]);
+    const float q0 = __fadd_rn(a0, __fmul_rn(c[2], p2));
+    const float q1 = __fadd_rn(a1, __fmul_rn(c[5], p2));
+    const float q2 = __fadd_rn(a2, __fmul_rn(c[8], p2));
+    const float r0 = __fmul_rn(q0, q2), r1 = __fmul_rn(q1, q2), r2 = q2;
+    const float gx = __fadd_rn(dot3_nofma(c[9], c[10], c[11], r0, r1, r2), c[21]);
+    const float gy = __fadd_rn(dot3_nofma(c[12], c[13], c[14], r0, r1, r2), c[22]);
+    const float gz = __fadd_rn(dot3_nofma(c[15], c[16], c[17], r0, r1, r2), c[23]);
+    plan_emit_point(gx, gy, gz, b, p, in, a, lane, copy);
   }
 }
 
@@ -198,7 +234,7 @@ plan_cells_kernel(PlanCellsArgs a) {
 // ---------------------------------------------------------------------------
 struct PlanScanArgs {
   const uint32_t* cnt;   // (n) per-key counts
-  const uint32_t* tsum;  // (tiles) totals per scan tile
+  const uint32_t* tsum;  // (kTsumCopies, tiles) totals per scan tile
   int n;                 // n_keys
   int tiles;
   int tile_shift;
@@ -213,9 +249,16 @@ plan_scan_kernel(PlanScanArgs a) {
   __shared__ int s_occ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
+  pdl_wait();
   // base of this tile: sum of the totals of the tiles before it
   uint32_t part = 0;
-  for (int j = tid; j < tile; j += kPlanThreads) part += __ldg(a.tsum + j);
+  for (int j = tid; j < tile; j += kPlanThreads) {
+    uint32_t v[kTsumCopies];
+#pragma unroll
+    for (int c = 0; c < kTsumCopies; ++c) v[c] = __ldg(a.tsum + c * a.tiles + j);     // independent loads
+#pragma unroll
+    for (int c = 0; c < kTsumCopies; ++c) part += v[c];
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if (lane == 0) s_warp[warp] = part;
@@ -293,145 +336,167 @@ plan_scan_kernel(PlanScanArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// P3: scatter + order.  Every kept point takes one slot of its key's run (the
-// cursor is the histogram itself, counted back down to zero -- the state the
-// next call expects, so the workspace cleans itself) and parks its id there;
-// the last point to arrive in a run (a second per-key counter tells) rewrites
-// the run in ascending point order as {cell, point} records.
+// P3: every kept point takes one slot of its key's run and parks {cell, id}
+// there.  The cursor is the histogram itself, counted back down to zero -- the
+// state the next call expects, so the workspace cleans itself.  Slot order
+// inside a run is arbitrary here; P4 fixes it.
 // ---------------------------------------------------------------------------
 struct PlanScatterArgs {
   const int32_t* key_of_point;
   const int32_t* cells;
   long long P;
   uint32_t* cnt;
-  uint32_t* done;
   const int32_t* key_start;
-  int n_keys;
-  int32_t* tmp;            // (P) ids in arrival order
-  int2* rec;               // (P) {output cell, point id} in (key, point id) order; {-1, 0} beyond K
+  int2* tmp;               // (P) {output cell, point id} in arrival order
   uint32_t* tsum;          // wiped for the next call
   int scan_tiles;
-  uint32_t* ctl;           // [0] CTA ticket, [1] n_long
-  int32_t* long_list;
-  KeyMap keys;
 };
-
-__device__ __forceinline__ int32_t ld_cg_i32(const int32_t* p) { return __ldcg(p); }
-
-// ascending order of a run of <= kRunSerial ids, in registers
-__device__ __forceinline__ void order_run_serial(const int32_t* tmp, int base, int n, int32_t cell, int2* rec) {
-  int32_t v[kRunSerial];
-#pragma unroll
-  for (int i = 0; i < kRunSerial; ++i) v[i] = (i < n) ? ld_cg_i32(tmp + base + i) : 0x7fffffff;
-#pragma unroll
-  for (int i = 0; i < kRunSerial; ++i) {
-    int r = 0;
-#pragma unroll
-    for (int j = 0; j < kRunSerial; ++j) r += (v[j] < v[i]) ? 1 : 0;
-    if (i < n) rec[base + r] = make_int2(cell, v[i]);
-  }
-}
-
-__device__ __forceinline__ void cmpxchg_asc(volatile int32_t* v, int i, int l) {
-  const int32_t x = v[i], y = v[l];
-  if (y < x) { v[i] = y; v[l] = x; }
-}
 
 __global__ void __launch_bounds__(kPlanThreads)
 plan_scatter_kernel(PlanScatterArgs a) {
-  __shared__ int32_t s_run[kPlanThreads / 32][kRunWarp];
-  __shared__ int s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
   if (blockIdx.x == 0)
-    for (int i = tid; i < a.scan_tiles; i += kPlanThreads) a.tsum[i] = 0u;
-  const long long p = (long long)blockIdx.x * kPlanThreads + tid;
-  int pend_base = 0, pend_n = 0;
-  int32_t pend_cell = 0;
-  if (p < a.P) {
-    const int K = __ldg(a.key_start + a.n_keys);
-    if (p >= K) a.rec[p] = make_int2(-1, 0);
-    const int32_t key = __ldg(a.key_of_point + p);
-    if (key >= 0) {
-      const int base = __ldg(a.key_start + key);
-      const int n = __ldg(a.key_start + key + 1) - base;
-      const int32_t cell = __ldg(a.cells + p);
-      if (n == 1) {                                    // alone in its voxel: nothing to order
-        a.rec[base] = make_int2(cell, static_cast<int32_t>(p));
-        a.cnt[key] = 0u;
-      } else {
-        const uint32_t slot = atomicSub(a.cnt + key, 1u) - 1u;
-        __stcg(a.tmp + base + static_cast<int>(slot), static_cast<int32_t>(p));
-        __threadfence();
-        const uint32_t fin = atomicAdd(a.done + key, 1u) + 1u;
-        if (fin == static_cast<uint32_t>(n)) {         // every id of the run is parked and visible
-          a.done[key] = 0u;
-          __threadfence();
-          if (n <= kRunSerial) order_run_serial(a.tmp, base, n, cell, a.rec);
-          else if (n <= kRunWarp) { pend_base = base; pend_n = n; pend_cell = cell; }
-          else a.long_list[atomicAdd(a.ctl + 1, 1u)] = key;
+    for (int i = threadIdx.x; i < a.scan_tiles * kTsumCopies; i += kPlanThreads) a.tsum[i] = 0u;
+  const long long p = (long long)blockIdx.x * kPlanThreads + threadIdx.x;
+  if (p >= a.P) return;
+  const int32_t key = __ldg(a.key_of_point + p);
+  if (key < 0) return;
+  const int32_t cell = __ldg(a.cells + p);
+  const int base = __ldg(a.key_start + key);
+  const int n = __ldg(a.key_start + key + 1) - base;
+  int slot = 0;
+  if (n == 1) a.cnt[key] = 0u;                         // alone in its voxel: no cursor needed
+  else slot = static_cast<int>(atomicSub(a.cnt + key, 1u)) - 1;
+  a.tmp[base + slot] = make_int2(cell, static_cast<int32_t>(p));
+}
+
+// ---------------------------------------------------------------------------
+// P4: ascending point order inside every run (== the stable sort order).
+// ---------------------------------------------------------------------------
+struct PlanOrderArgs {
+  const int2* tmp;            // (P) {cell, id} in arrival order; first K valid
+  const int32_t* key_start;   // only key_start[n_keys] = K is read here (and bounds of long runs)
+  int n_keys;
+  long long P;
+  int2* rec;                  // (P) {cell, id} in (key, id) order; {-1, 0} beyond K
+  KeyMap keys;
+};
+
+__device__ __forceinline__ void cmpxchg_asc_y(volatile int2* v, int i, int l) {
+  const int32_t x = v[i].y, y = v[l].y;
+  if (y < x) { v[i].y = y; v[l].y = x; }
+}
+
+__global__ void __launch_bounds__(kPlanThreads)
+plan_order_kernel(PlanOrderArgs a) {
+  __shared__ int32_t s_run[kPlanThreads / 32][kRunWarp];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
+  const int K = __ldg(a.key_start + a.n_keys);
+  const long long i = (long long)blockIdx.x * kPlanThreads + tid;
+  int pend_start = 0, pend_n = 0;
+  if (i < a.P) {
+    if (i >= K) {
+      a.rec[i] = make_int2(-1, 0);
+    } else {
+      const int ii = static_cast<int>(i);
+      const int2 me = __ldg(a.tmp + ii);
+      // the run of this slot = the neighbours with the same cell; count the smaller ids on the way.
+      // The four neighbours on either side are loaded up front (independent loads, one round trip:
+      // most runs are that short); only longer runs continue with a dependent scan.
+      constexpr int kWin = 4;
+      int2 lw[kWin], rw[kWin];
+#pragma unroll
+      for (int k = 0; k < kWin; ++k) {
+        lw[k] = make_int2(-2, 0); rw[k] = make_int2(-2, 0);          // -2: no such slot (cells are >= 0)
+        if (ii - 1 - k >= 0) lw[k] = __ldg(a.tmp + ii - 1 - k);
+        if (ii + 1 + k < K) rw[k] = __ldg(a.tmp + ii + 1 + k);
+      }
+      int rank = 0, left = 0, right = 0;
+      bool lgo = true, rgo = true;
+#pragma unroll
+      for (int k = 0; k < kWin; ++k) {
+        lgo = lgo && lw[k].x == me.x;
+        rgo = rgo && rw[k].x == me.x;
+        rank += (lgo && lw[k].y < me.y) ? 1 : 0;
+        rank += (rgo && rw[k].y < me.y) ? 1 : 0;
+        left += lgo ? 1 : 0;
+        right += rgo ? 1 : 0;
+      }
+      if (lgo)
+        for (int j = ii - 1 - kWin; j >= 0 && left < kRunSerial; --j) {
+          const int2 o = __ldg(a.tmp + j);
+          if (o.x != me.x) break;
+          rank += (o.y < me.y) ? 1 : 0;
+          ++left;
         }
+      if (rgo)
+        for (int j = ii + 1 + kWin; j < K && right < kRunSerial; ++j) {
+          const int2 o = __ldg(a.tmp + j);
+          if (o.x != me.x) break;
+          rank += (o.y < me.y) ? 1 : 0;
+          ++right;
+        }
+      if (left + right + 1 <= kRunSerial) {
+        a.rec[ii - left + rank] = me;
+      } else if (left == 0) {
+        // first slot of a long run (every slot of the run takes this branch or does nothing):
+        // its length comes from the interval table
+        const uint32_t key = a.keys.key_of_cell(static_cast<uint32_t>(me.x));
+        pend_start = ii;
+        pend_n = __ldg(a.key_start + key + 1) - ii;
       }
     }
   }
-  // runs of 9 .. 256 points: the finisher's warp orders them, one run at a time
+  // runs of more than kRunSerial points: the warp of the run's first slot orders them, one run at a time
   uint32_t pend = __ballot_sync(0xffffffffu, pend_n > 0);
   while (pend) {
     const int src = __ffs(pend) - 1;
     pend &= pend - 1;
-    const int base = __shfl_sync(0xffffffffu, pend_base, src);
+    const int start = __shfl_sync(0xffffffffu, pend_start, src);
     const int n = __shfl_sync(0xffffffffu, pend_n, src);
-    const int32_t cell = __shfl_sync(0xffffffffu, pend_cell, src);
+    const int32_t cell = __ldg(&a.tmp[start].x);
     __syncwarp();
-    for (int i = lane; i < n; i += 32) s_run[warp][i] = ld_cg_i32(a.tmp + base + i);
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      const int32_t v = s_run[warp][i];
-      int r = 0;
-      for (int j = 0; j < n; ++j) r += (s_run[warp][j] < v) ? 1 : 0;
-      a.rec[base + r] = make_int2(cell, v);
-    }
-  }
-  // runs of more than 256 points (adversarial inputs: everything in a few voxels): the last CTA
-  // of the grid sorts them one after the other with a bitonic network whose compare-exchanges
-  // all point the same way, so the virtual +inf padding never has to move
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const uint32_t t = atomicAdd(a.ctl, 1u);
-    s_last = (t == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int n_long = static_cast<int>(*reinterpret_cast<volatile uint32_t*>(a.ctl + 1));
-  for (int r = 0; r < n_long; ++r) {
-    const int32_t key = ld_cg_i32(a.long_list + r);
-    const int s = a.key_start[key], n = a.key_start[key + 1] - s;
-    const int32_t cell = a.keys.cell_of_key(static_cast<uint32_t>(key));
-    volatile int32_t* v = a.tmp + s;
-    int n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    for (int k = 2; k <= n2; k <<= 1) {
-      const int half = k >> 1;
-      for (int t = tid; t < (n2 >> 1); t += kPlanThreads) {
-        const int blk = t / half, r0 = t - blk * half;
-        const int i = blk * k + r0, l = blk * k + (k - 1 - r0);
-        if (l < n) cmpxchg_asc(v, i, l);
+    if (n <= kRunWarp) {
+      // up to 256 points: ids into shared memory, every lane counts the smaller ones of its ids
+      for (int k = lane; k < n; k += 32) s_run[warp][k] = __ldg(&a.tmp[start + k].y);
+      __syncwarp();
+      for (int k = lane; k < n; k += 32) {
+        const int32_t v = s_run[warp][k];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += (s_run[warp][j] < v) ? 1 : 0;
+        a.rec[start + r] = make_int2(cell, v);
       }
-      __syncthreads();
-      for (int j = k >> 2; j > 0; j >>= 1) {
-        for (int t = tid; t < (n2 >> 1); t += kPlanThreads) {
-          const int blk = t / j, r0 = t - blk * j;
-          const int i = blk * 2 * j + r0, l = i + j;
-          if (l < n) cmpxchg_asc(v, i, l);
+    } else {
+      // longer (adversarial inputs: everything in a few voxels): bitonic network in place in the output,
+      // all compare-exchanges pointing the same way, so the virtual +inf padding never has to move
+      volatile int2* v = a.rec + start;
+      for (int k = lane; k < n; k += 32) { v[k].x = cell; v[k].y = a.tmp[start + k].y; }
+      __threadfence_block();
+      __syncwarp();
+      int n2 = 1;
+      while (n2 < n) n2 <<= 1;
+      for (int k = 2; k <= n2; k <<= 1) {
+        const int half = k >> 1;
+        for (int t = lane; t < (n2 >> 1); t += 32) {
+          const int blk = t / half, r0 = t - blk * half;
+          const int x = blk * k + r0, l = blk * k + (k - 1 - r0);
+          if (l < n) cmpxchg_asc_y(v, x, l);
         }
-        __syncthreads();
+        __threadfence_block();
+        __syncwarp();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+          for (int t = lane; t < (n2 >> 1); t += 32) {
+            const int blk = t / j, r0 = t - blk * j;
+            const int x = blk * 2 * j + r0, l = x + j;
+            if (l < n) cmpxchg_asc_y(v, x, l);
+          }
+          __threadfence_block();
+          __syncwarp();
+        }
       }
     }
-    for (int i = tid; i < n; i += kPlanThreads) a.rec[s + i] = make_int2(cell, v[i]);
-    __syncthreads();
   }
-  if (tid == 0) { a.ctl[0] = 0u; a.ctl[1] = 0u; }
 }
 
 }  // namespace lss

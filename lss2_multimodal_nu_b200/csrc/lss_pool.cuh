@@ -85,6 +85,7 @@ feat_stage_kernel(const void* __restrict__ feat, long long feat_bs, int dtype, i
                   float* __restrict__ feat_t) {
   __shared__ float tile[32][33];
   const int bn = blockIdx.z;
+  pdl_wait();
   const size_t sbase = (size_t)bn * feat_bs;
   float* dst = feat_t + (size_t)bn * HW * C;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -188,7 +189,7 @@ constexpr int kZeroBytes = 2048;  // zero block in shared memory: source of the 
 #define LSS_FWD_MINB 3
 #endif
 #ifndef LSS_FWD_M
-#define LSS_FWD_M 1
+#define LSS_FWD_M 2
 #endif
 #ifndef LSS_BWD_MINB
 #define LSS_BWD_MINB 2
@@ -273,18 +274,25 @@ pool_fwd_kernel(PoolFwdArgs a) {
   constexpr int NR = kW * 32;
   constexpr int S = kM * 32 / G;        // records per walker (a divisor of 32 or 64)
   constexpr int U = 4;                  // walk steps whose gathers are issued together
-  static_assert(S >= 1 && (S <= 32 ? 32 % S == 0 : S == 64), "a walker's share must not straddle mask words unevenly");
+  static_assert(S >= 1 && (S <= 32 ? 32 % S == 0 : S == 64), "a walker's share is a whole number of mask words or a divisor of one");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   __shared__ __align__(128) float4 s_zero[kZeroBytes / 16];
+  pdl_wait();
   if (static_cast<int>(blockIdx.x) < a.fill_ctas) {
+#ifndef LSS_DBG_FWD_NOFILL
     pool_fill_zeros(a, s_zero);
+#endif
     return;
   }
+#ifdef LSS_DBG_FWD_NOREDUCE
+  return;
+#endif
 
   // ======================= REDUCE: segmented sums over the sorted records ==============
-  __shared__ uint2 s_rec[kPoolWarps][NR + G];               // {row offset (16-byte units) | head << 31, depth bits}
-  __shared__ int s_cell[kPoolWarps][NR];
+  // staged record: {feature-row offset in 16-byte units, depth bits, cell if the record opens an
+  // interval that is not its walker's first else -1, unused}
+  __shared__ uint4 s_rec[kPoolWarps][NR + G];
   const long long i0 = ((long long)(blockIdx.x - a.fill_ctas) * kPoolWarps + warp) * (kM * 32);
   if (i0 >= a.P) return;
   // ---- one round of loads: the chunk's and the look-ahead word's records ----
@@ -297,7 +305,7 @@ pool_fwd_kernel(PoolFwdArgs a) {
   }
   int before = -1;
   if (lane == 0 && i0 > 0) before = __ldg(&a.rec[i0 - 1].x);
-  uint32_t H[kW], HV[kW];                                   // heads (cell differs from its predecessor), valid heads
+  uint32_t H[kW], HV[kW], T[kW];                            // heads (cell differs from its predecessor), valid heads, terminator
 #pragma unroll
   for (int w = 0; w < kW; ++w) {
     int prev = __shfl_up_sync(0xffffffffu, cell[w], 1);
@@ -305,30 +313,19 @@ pool_fwd_kernel(PoolFwdArgs a) {
     before = __shfl_sync(0xffffffffu, cell[w], 31);         // predecessor of the next word's lane 0
     H[w] = __ballot_sync(0xffffffffu, cell[w] != prev);
     HV[w] = H[w] & __ballot_sync(0xffffffffu, cell[w] >= 0);
+    T[w] = H[w] & ~HV[w];
   }
   // ---- walker of this lane: records [r0, end) ----
   const int g = lane / L, sub = lane % L;
   const int lo_bit = g * S;                                  // first record of the walker's share
-  int r0, end;
-  {
-    uint32_t m;
-    if (S >= 32) {                                           // share = whole words
-      r0 = NR;
-#pragma unroll
-      for (int w = (S / 32) - 1; w >= 0; --w) {
-        const uint32_t b = HV[(lo_bit >> 5) + w < kW ? (lo_bit >> 5) + w : 0];
-        if (b) r0 = ((lo_bit >> 5) + w) * 32 + __ffs(b) - 1;
-      }
-      m = r0 < NR ? 1u : 0u;
-    } else {
-      const uint32_t mask = ((S == 32) ? 0xffffffffu : ((1u << (S & 31)) - 1u)) << (lo_bit & 31);
-      m = 0u;
-#pragma unroll
-      for (int w = 0; w < kM; ++w) if ((lo_bit >> 5) == w) m = HV[w] & mask;
-      r0 = (lo_bit & ~31) + __ffs(m) - 1;
-    }
-    end = first_bit_from<kW>(H, lo_bit + S);
-    if (!m) { r0 = 0; end = 0; }
+  int r0 = first_bit_from<kW>(HV, lo_bit);                   // first interval that starts in the share
+  int end = 0;
+  if (r0 < lo_bit + S) {
+    // the walker runs to the first head at or after the end of its share; the kept records are a
+    // prefix of the list, so the first dropped one (a head that is not valid) ends everything
+    end = min(first_bit_from<kW>(H, lo_bit + S), first_bit_from<kW>(T, r0 + 1));
+  } else {
+    r0 = 0;
   }
   const int n_g = end - r0;
   const bool overflow = n_g > 0 && end == NR;                // the last interval runs past the look-ahead
@@ -357,75 +354,87 @@ pool_fwd_kernel(PoolFwdArgs a) {
       }
       // a walker's first record opens its first interval: nothing to close there
       bool head = (H[w] >> lane) & 1u;
-      if (w < kM) {
-        const int gs = r / S;                                 // walker whose share holds r
-        uint32_t share = HV[w];
-        if (S < 32) share &= ((1u << (S & 31)) - 1u) << ((gs * S) & 31);
-        bool first_of_share = (share & (0u - share)) == (1u << lane);
-        if (S > 32) first_of_share = first_of_share && (w == 0 || HV[0] == 0u);
-        if (first_of_share) head = false;
+      if (w < kM && head) {
+        const int share_lo = (r / S) * S;                     // share that holds r
+        if (first_bit_from<kW>(HV, share_lo) == r) head = false;
       }
-      s_rec[warp][r] = make_uint2(off16 | (head ? 0x80000000u : 0u), __float_as_uint(dv));
-      s_cell[warp][r] = cell[w];
+      s_rec[warp][r] = make_uint4(off16, __float_as_uint(dv), head ? static_cast<uint32_t>(cell[w]) : 0xffffffffu, 0u);
     }
   }
   __syncwarp();
   // padding record of the walker: its own last record with weight zero (re-gathers a row it has
   // already summed, adds 0 * row), for the steps after its end while other walkers still run
   if (sub == 0) {
-    uint2 pad = make_uint2(0u, 0u);
-    if (n_g > 0) pad = make_uint2(s_rec[warp][end - 1].x & 0x7fffffffu, 0u);
+    uint4 pad = make_uint4(0u, 0u, 0xffffffffu, 0u);
+    if (n_g > 0) pad.x = s_rec[warp][end - 1].x;
     s_rec[warp][NR + g] = pad;
   }
   __syncwarp();
 
   const uint32_t vsub = (static_cast<int>(sub) < a.nact) ? sub : 0u;   // idle lanes shadow lane 0, never store
-  const bool storer = n_g > 0 && static_cast<int>(sub) < a.nact;
+  const bool storer = static_cast<int>(sub) < a.nact;
   const char* src = reinterpret_cast<const char*>((kFused ? a.feat_t : a.x) + vsub * 4);
   const char* src2 = reinterpret_cast<const char*>((kFused ? a.feat_t : a.x) + 4 * L * kNP + vsub * 2);
   float* out = a.bev + vsub * 4;
   float* out2 = a.bev + 4 * L * kNP + vsub * 2;
-  const uint2* recs = s_rec[warp];
+  const uint4* recs = s_rec[warp];
+  const uint32_t Cw = static_cast<uint32_t>(a.C);
 
   float4 acc[kNP > 0 ? kNP : 1];
   float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int p = 0; p < kNP; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int cur = (n_g > 0) ? s_cell[warp][r0] : 0;
-  auto close = [&](int next_cell) {
+  // output cell of the walker's first interval: its first record carries -1 (no close), so take it
+  // from the cell registers of the lane that loaded it
+  int cur;
+  {
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      const int t = __shfl_sync(0xffffffffu, cell[w], r0 & 31);
+      if ((r0 >> 5) == w) c = t;
+    }
+    cur = c;
+  }
+  auto store_acc = [&]() {
     if (storer) {
-      float* o = out + (size_t)cur * a.C;
+      float* o = out + (size_t)static_cast<uint32_t>(cur) * Cw;
 #pragma unroll
       for (int p = 0; p < kNP; ++p) *reinterpret_cast<float4*>(o + p * 4 * L) = acc[p];
-      if (kT2) *reinterpret_cast<float2*>(out2 + (size_t)cur * a.C) = acc2;
+      if (kT2) *reinterpret_cast<float2*>(out2 + (size_t)static_cast<uint32_t>(cur) * Cw) = acc2;
     }
-#pragma unroll
-    for (int p = 0; p < kNP; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc2 = make_float2(0.f, 0.f);
-    cur = next_cell;
   };
 
   for (int t0 = 0; t0 < n_max; t0 += U) {
-    uint2 rc[U];
-    int ri[U];
+    uint4 rc[U];
     float4 f[U][kNP > 0 ? kNP : 1];
     float2 f2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      ri[u] = (t0 + u < n_g) ? r0 + t0 + u : NR + g;
-      rc[u] = recs[ri[u]];
-      const size_t byte = (size_t)(rc[u].x & 0x7fffffffu) << 4;
+      rc[u] = recs[(t0 + u < n_g) ? r0 + t0 + u : NR + g];
+#ifdef LSS_DBG_FWD_ROW0
+      rc[u].x = 0u;
+#endif
+      const char* row = src + ((size_t)rc[u].x << 4);
 #pragma unroll
-      for (int p = 0; p < kNP; ++p) f[u][p] = __ldg(reinterpret_cast<const float4*>(src + byte) + p * L);
-      if (kT2) f2[u] = __ldg(reinterpret_cast<const float2*>(src2 + byte));
+      for (int p = 0; p < kNP; ++p) f[u][p] = __ldg(reinterpret_cast<const float4*>(row) + p * L);
+      if (kT2) f2[u] = __ldg(reinterpret_cast<const float2*>(src2 + ((size_t)rc[u].x << 4)));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (static_cast<int>(rc[u].x) < 0) close(s_cell[warp][ri[u]]);
       const float dv = __uint_as_float(rc[u].y);
+      if (static_cast<int>(rc[u].z) >= 0) {                   // the record opens a new interval: close the running one
+        store_acc();
+        cur = static_cast<int>(rc[u].z);
 #pragma unroll
-      for (int p = 0; p < kNP; ++p) f4_fma(dv, f[u][p], acc[p]);
-      if (kT2) { acc2.x = fmaf(dv, f2[u].x, acc2.x); acc2.y = fmaf(dv, f2[u].y, acc2.y); }
+        for (int p = 0; p < kNP; ++p)
+          acc[p] = make_float4(dv * f[u][p].x, dv * f[u][p].y, dv * f[u][p].z, dv * f[u][p].w);
+        if (kT2) acc2 = make_float2(dv * f2[u].x, dv * f2[u].y);
+      } else {
+#pragma unroll
+        for (int p = 0; p < kNP; ++p) f4_fma(dv, f[u][p], acc[p]);
+        if (kT2) { acc2.x = fmaf(dv, f2[u].x, acc2.x); acc2.y = fmaf(dv, f2[u].y, acc2.y); }
+      }
     }
   }
   // ---- an interval longer than the look-ahead (adversarial inputs): follow it to its end ----
@@ -454,7 +463,7 @@ pool_fwd_kernel(PoolFwdArgs a) {
       }
     }
   }
-  if (n_g > 0) close(0);
+  if (n_g > 0) store_acc();
 }
 
 // --------------------------------------------------------------------------
@@ -486,16 +495,19 @@ pool_dense_bwd_nhwc_kernel(const float4* __restrict__ dbev, const int32_t* __res
 // line.  For every kept point the voxel gradient g (one contiguous line of the
 // channels-innermost dBEV) is gathered once and used twice:
 //     d_depth[d] = <g, feat>      d_feat += depth[d] * g
-// Only OCCUPIED voxels of dBEV are ever read.  <g, feat> has C terms of order one
-// that cancel, so it is accumulated in float64 -- but without the float32 ->
-// float64 conversion instruction, which runs at a sixteenth of the FMA rate on
-// this part and was the limiter of the previous version of this kernel: the 32
-// bits of g are re-packed with three integer operations into the float64 whose
-// value is g * 2^-896 exactly (sign | exponent | mantissa shifted by three bits;
-// zero stays zero, denormals stay exact), and the finished dot is scaled back by
-// 2^896.  The kU partial dots of a lane are reduced together with a transposed
-// butterfly.  There are no atomics: the depth slices' partial d_feat meet in
-// shared memory in a fixed order, results are bit-reproducible.
+// Only OCCUPIED voxels of dBEV are ever read.  A round handles kU depth bins: the
+// first kU lanes of a walker hold {cell, depth} of the round's bins (loaded one
+// round ahead) and hand them out by shuffle, the kU gathers are issued together.
+// <g, feat> has C terms of order one that cancel, so it is accumulated in
+// float64 -- but without the float32 -> float64 conversion instruction, which
+// runs at a sixteenth of the FMA rate on this part and was the limiter of the
+// first version of this kernel: the 32 bits of g are re-packed with three integer
+// operations into the float64 whose value is g * 2^-896 exactly (sign |
+// exponent | mantissa shifted by three bits; zero stays zero, denormals stay
+// exact), and the finished dot is scaled back by 2^896.  The kU partial dots of a
+// lane are reduced together with a transposed butterfly.  There are no atomics:
+// the depth slices' partial d_feat meet in shared memory in a fixed order,
+// results are bit-reproducible.
 // A non-finite upstream gradient still reaches the outputs: d_feat sees it
 // through the float32 FMA, and a walker whose d_feat partial is not finite
 // writes NaN to the d_depth bins of its slice.
@@ -514,14 +526,13 @@ struct PoolBwdArgs {
   int softmax;              // 1: depth = softmax(logits); emit d_logits = p * (d_depth - sum_d p * d_depth)
   int D, fH, fW, C, BN;
   int nact;                 // lanes of a walker that own channels
-  int rg_warps;             // warps of a CTA along the rows (power of two <= 8); the other 8/rg_warps slice D
+  int rg_warps;             // warps of a CTA along the rows; the CTA's other warps slice D
+  int slices;               // depth slices (warps per row group)
   int d_per_slice;
   int row_blocks;           // CTAs per image column: ceil(fH / (G * rg_warps))
 };
 
-constexpr int kBwdThreads = 256;
-constexpr int kBwdWarps = kBwdThreads / 32;
-constexpr int kBwdChunk = 32;    // depth bins staged per walker at a time
+constexpr int kBwdMaxWarps = 8;
 constexpr int kBwdMaxD = 128;    // softmax backward keeps a pixel's d_depth in shared memory
 
 // the float64 whose value is x * 2^-896 (exact for every finite float32, zero -> zero)
@@ -531,20 +542,20 @@ __device__ __forceinline__ double f32_as_scaled_f64(float x) {
 }
 
 template <int L, int kNP, bool kT2, bool kGeneral>
-__global__ void __launch_bounds__(kBwdThreads, LSS_BWD_MINB)
+__global__ void __launch_bounds__(32 * kBwdMaxWarps, (4 * kNP + (kT2 ? 2 : 0)) <= 4 ? 4 : LSS_BWD_MINB)
 liftsplat_bwd_kernel(PoolBwdArgs a) {
   constexpr int G = 32 / L;                     // pixels (walkers) per warp
-  constexpr int U = 4;                          // depth bins per round
-  constexpr int kLog = L == 32 ? 5 : L == 16 ? 4 : L == 8 ? 3 : L == 4 ? 2 : L == 2 ? 1 : 0;
-  constexpr int kLogU = kLog < 2 ? kLog : 2;    // exchange levels that halve the live dots
   constexpr int kV = 4 * kNP + (kT2 ? 2 : 0);   // channels per lane
-  static_assert(kBwdChunk % U == 0, "chunk must hold whole rounds");
-  __shared__ int2 s_cd[kBwdWarps][G][kBwdChunk];             // {output cell, depth bits (0 if dropped)}
-  __shared__ float s_df[kBwdWarps][G * (L * kV)];            // the warp's partial d_feat
-  __shared__ float s_dd[kGeneral ? G * kBwdWarps : 1][kGeneral ? kBwdMaxD : 1];   // d_depth of the CTA's pixels (softmax)
+  constexpr int U = (kV <= 4 && L >= 8) ? 8 : 4;   // depth bins per round (U <= L)
+  constexpr int kLog = L == 32 ? 5 : L == 16 ? 4 : 3;
+  constexpr int kLogU = U == 8 ? 3 : 2;         // exchange levels that halve the live dots (kLogU <= kLog)
+  static_assert(L >= 8 && U <= L, "a walker's first U lanes hold the round's bins");
+  __shared__ float s_df[kBwdMaxWarps][G * (L * kV)];         // the warp's partial d_feat
+  __shared__ float s_dd[kGeneral ? G * kBwdMaxWarps : 1][kGeneral ? kBwdMaxD : 1];   // d_depth of the CTA's pixels (softmax)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / L, sub = lane % L;
+  pdl_wait();
   // CTA -> (image column, block of rows); warp -> (row group, depth slice)
   const int col = blockIdx.x / a.row_blocks, rb = blockIdx.x - col * a.row_blocks;
   const int bn = col / a.fW, w = col - bn * a.fW;
@@ -558,8 +569,35 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
   const bool lane_act = sub < a.nact;
   const int vsub = lane_act ? sub : 0;
 
+  // {cell, depth} of the bin this lane holds for the coming round (lanes sub < U of every walker)
+  const size_t pbase = (size_t)bn * a.D * HW + hw;           // cells index of (bn, d = 0, h, w)
+  const size_t dbase = (size_t)bn * a.depth_bs + hw;
+  auto load_bin = [&](int d, int& c, float& dv) {
+    c = -1; dv = 0.f;
+    if (sub < U && d < d_hi && pix_ok) {
+      c = __ldg(a.cells + pbase + (size_t)d * HW);
+      dv = load_as_float(a.depth, dbase + (size_t)d * HW, a.depth_dtype);
+    }
+  };
+  int ncell;
+  float ndv;
+  load_bin(d_lo + sub, ncell, ndv);
+#ifdef LSS_BWD_PREFETCH
+  // the voxel lines of the whole slice are requested from DRAM now, all at once (L2 prefetch): the
+  // rounds below then find them in L2 instead of paying one DRAM round trip per round
+  for (int d = d_lo + sub; d < d_hi; d += L) {
+    if (pix_ok) {
+      const int c = __ldg(a.cells + pbase + (size_t)d * HW);
+      if (c >= 0) {
+        const char* line = reinterpret_cast<const char*>(a.dbev + (size_t)c * a.C);
+        for (int b = 0; b < a.C * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(line + b));
+      }
+    }
+  }
+#endif
+
   // the pixel's context vector, float64
-  double fd[kV > 0 ? kV : 1];
+  double fd[kV];
   {
     const float* frow = a.feat_t + ((size_t)bn * HW + hw) * a.C;
 #pragma unroll
@@ -576,7 +614,7 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
       for (int v = 0; v < kV; ++v) fd[v] = 0.0;
     }
   }
-  float acc[kV > 0 ? kV : 1];
+  float acc[kV];
 #pragma unroll
   for (int v = 0; v < kV; ++v) acc[v] = 0.f;
 
@@ -585,100 +623,80 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
 #pragma unroll
   for (int k = 0; k < kLogU; ++k)
     if (sub & (L >> (k + 1))) my_u += U >> (k + 1);
-  const bool writer = (kLog == kLogU) ? true : (sub & ((L >> kLogU) - 1)) == 0;
-  constexpr int kDots = (kLog >= 2) ? 1 : (kLog == 1 ? 2 : 4);   // dots a writer holds per round
+  const bool writer = (sub & ((L >> kLogU) - 1)) == 0;
 
   const float* gsrc = a.dbev + vsub * 4;
   const float* gsrc2 = a.dbev + 4 * L * kNP + vsub * 2;
-  const size_t pbase = (size_t)bn * a.D * HW + hw;           // cells index of (bn, d = 0, h, w)
-  const size_t dbase = (size_t)bn * a.depth_bs + hw;
-  int2 (*cd)[kBwdChunk] = s_cd[warp];
+  const uint32_t Cw = static_cast<uint32_t>(a.C);
 
-  for (int dc = d_lo; dc < d_hi; dc += kBwdChunk) {
-    const int nd = min(kBwdChunk, d_hi - dc);
-    __syncwarp();
-    // stage {cell, depth} of the warp's G pixels x nd bins: lane -> (pixel e / 32... ) one bin each
+  for (int d0 = d_lo; d0 < d_hi; d0 += U) {
+    const int ccell = ncell;
+    const float cdv = (ccell >= 0) ? ndv : 0.f;             // dropped point: weight zero
+    load_bin(d0 + U + sub, ncell, ndv);                      // next round's bins, one round ahead
+    float4 gq[U][kNP > 0 ? kNP : 1];
+    float2 g2[U];
+    float dv[U];
 #pragma unroll
-    for (int e = lane; e < G * kBwdChunk; e += 32) {
-      const int gp = e / kBwdChunk, dl = e - gp * kBwdChunk;
-      int2 v = make_int2(-1, 0);                            // padding / dropped point: weight zero
-      const int hh = h - g + gp;                            // row of walker gp
-      if (dl < nd && hh < a.fH) {
-        const long long o = (long long)(dc + dl) * HW + (long long)(gp - g) * a.fW;
-        v.x = __ldg(a.cells + (long long)pbase + o);
-        if (v.x >= 0) v.y = __float_as_int(load_as_float(a.depth, (size_t)((long long)dbase + o), a.depth_dtype));
-      }
-      cd[gp][dl] = v;
+    for (int u = 0; u < U; ++u) {
+#ifdef LSS_DBG_BWD_CELL0
+      const int c = 0 * __shfl_sync(0xffffffffu, ccell, g * L + u);
+#else
+      const int c = __shfl_sync(0xffffffffu, ccell, g * L + u);
+#endif
+      dv[u] = __shfl_sync(0xffffffffu, cdv, g * L + u);
+      const float* row = gsrc + (size_t)static_cast<uint32_t>(max(c, 0)) * Cw;   // dropped: any valid line, weight zero
+#pragma unroll
+      for (int p = 0; p < kNP; ++p) gq[u][p] = __ldg(reinterpret_cast<const float4*>(row) + p * L);
+      if (kT2) g2[u] = __ldg(reinterpret_cast<const float2*>(gsrc2 + (size_t)static_cast<uint32_t>(max(c, 0)) * Cw));
     }
-    __syncwarp();
-    const int nd_pad = (nd + U - 1) / U * U;
-    for (int d0 = 0; d0 < nd_pad; d0 += U) {
-      float4 gq[U][kNP > 0 ? kNP : 1];
-      float2 g2[U];
-      float dv[U];
+    double dot[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int2 v = cd[g][d0 + u];
-        dv[u] = __int_as_float(v.y);
-        const size_t off = (size_t)max(v.x, 0) * a.C;       // dropped: any valid line, weight zero
+    for (int u = 0; u < U; ++u) {
+      double s = 0.0;
 #pragma unroll
-        for (int p = 0; p < kNP; ++p) gq[u][p] = __ldg(reinterpret_cast<const float4*>(gsrc + off) + p * L);
-        if (kT2) g2[u] = __ldg(reinterpret_cast<const float2*>(gsrc2 + off));
-      }
-      double dot[U];
+      for (int p = 0; p < kNP; ++p) {
+        const float gv[4] = {gq[u][p].x, gq[u][p].y, gq[u][p].z, gq[u][p].w};
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        double s = 0.0;
-#pragma unroll
-        for (int p = 0; p < kNP; ++p) {
-          const float gv[4] = {gq[u][p].x, gq[u][p].y, gq[u][p].z, gq[u][p].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            s = fma(f32_as_scaled_f64(gv[k]), fd[4 * p + k], s);
-            acc[4 * p + k] = fmaf(dv[u], gv[k], acc[4 * p + k]);
-          }
-        }
-        if (kT2) {
-          s = fma(f32_as_scaled_f64(g2[u].x), fd[4 * kNP], s);
-          s = fma(f32_as_scaled_f64(g2[u].y), fd[4 * kNP + 1], s);
-          acc[4 * kNP] = fmaf(dv[u], g2[u].x, acc[4 * kNP]);
-          acc[4 * kNP + 1] = fmaf(dv[u], g2[u].y, acc[4 * kNP + 1]);
-        }
-        dot[u] = s;
-      }
-      // transposed butterfly over the walker's L lanes: halve the number of live dots per exchange
-#pragma unroll
-      for (int k = 0; k < kLog; ++k) {
-        const int o = L >> (k + 1);
-        if (k < kLogU) {
-          const int half = U >> (k + 1);
-          const bool upper = (sub & o) != 0;
-#pragma unroll
-          for (int i = 0; i < half; ++i) {
-            const double send = upper ? dot[i] : dot[i + half];
-            const double keep = upper ? dot[i + half] : dot[i];
-            dot[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-          }
-        } else {
-          dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
+        for (int k = 0; k < 4; ++k) {
+          s = fma(f32_as_scaled_f64(gv[k]), fd[4 * p + k], s);
+          acc[4 * p + k] = fmaf(dv[u], gv[k], acc[4 * p + k]);
         }
       }
-      if (writer && pix_ok) {
-#pragma unroll
-        for (int i = 0; i < kDots; ++i) {
-          const int dl = d0 + my_u + i;
-          if (dl < nd) {
-            const int d = dc + dl;
-            // 2^896: back from the scaled domain; dropped points (weight zero, foreign line) give 0
-            float r = static_cast<float>(dot[i] * 5.2829453113566525e269);
-            if (cd[g][dl].x < 0) r = 0.f;
-            const size_t o = (size_t)bn * a.ddepth_bs + (size_t)d * HW + hw;
-            if (!kGeneral) reinterpret_cast<float*>(a.ddepth)[o] = r;
-            else if (a.softmax) s_dd[rg * G + g][d] = r;      // D <= kBwdMaxD (host)
-            else store_from_float(a.ddepth, o, r, a.out_dtype);
-          }
-        }
+      if (kT2) {
+        s = fma(f32_as_scaled_f64(g2[u].x), fd[4 * kNP], s);
+        s = fma(f32_as_scaled_f64(g2[u].y), fd[4 * kNP + 1], s);
+        acc[4 * kNP] = fmaf(dv[u], g2[u].x, acc[4 * kNP]);
+        acc[4 * kNP + 1] = fmaf(dv[u], g2[u].y, acc[4 * kNP + 1]);
       }
+      dot[u] = s;
+    }
+    // transposed butterfly over the walker's L lanes: halve the number of live dots per exchange
+#pragma unroll
+    for (int k = 0; k < kLog; ++k) {
+      const int o = L >> (k + 1);
+      if (k < kLogU) {
+        const int half = U >> (k + 1);
+        const bool upper = (sub & o) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const double send = upper ? dot[i] : dot[i + half];
+          const double keep = upper ? dot[i + half] : dot[i];
+          dot[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      } else {
+        dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
+      }
+    }
+    const int wcell = __shfl_sync(0xffffffffu, ccell, g * L + my_u);
+    const int d = d0 + my_u;
+    if (writer && pix_ok && d < d_hi) {
+      // 2^896: back from the scaled domain; dropped points (weight zero, foreign line) give 0
+      float r = static_cast<float>(dot[0] * 5.282945311356653e269);
+      if (wcell < 0) r = 0.f;
+      const size_t o = (size_t)bn * a.ddepth_bs + (size_t)d * HW + hw;
+      if (!kGeneral) reinterpret_cast<float*>(a.ddepth)[o] = r;
+      else if (a.softmax) s_dd[rg * G + g][d] = r;            // D <= kBwdMaxD (host)
+      else store_from_float(a.ddepth, o, r, a.out_dtype);
     }
   }
   // a non-finite gradient line shows in the float32 partial d_feat: poison this slice's d_depth
@@ -704,23 +722,21 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
     float* mine = s_df[warp] + g * (L * kV);
 #pragma unroll
     for (int p = 0; p < kNP; ++p)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) mine[p * 4 * L + sub * 4 + k] = acc[4 * p + k];
-    if (kT2) { mine[4 * L * kNP + sub * 2] = acc[4 * kNP]; mine[4 * L * kNP + sub * 2 + 1] = acc[4 * kNP + 1]; }
+      *reinterpret_cast<float4*>(mine + p * 4 * L + sub * 4) = make_float4(acc[4 * p], acc[4 * p + 1], acc[4 * p + 2], acc[4 * p + 3]);
+    if (kT2) *reinterpret_cast<float2*>(mine + 4 * L * kNP + sub * 2) = make_float2(acc[4 * kNP], acc[4 * kNP + 1]);
   }
   __syncthreads();
   {
-    const int n_slices = kBwdWarps / a.rg_warps;
     const int rows = a.rg_warps * G;                         // pixel rows of this CTA
     // consecutive threads -> consecutive rows (the contiguous direction of the output is w, which
     // a column CTA does not span), channels outer
-    for (int i = threadIdx.x; i < rows * a.C; i += kBwdThreads) {
+    for (int i = threadIdx.x; i < rows * a.C; i += blockDim.x) {
       const int r = i % rows, c = i / rows;
       const int hh = rb * rows + r;
       if (hh >= a.fH) continue;
       const int wg = r / G, gg = r - wg * G;                 // row group (warp along rows), walker
       float s = 0.f;
-      for (int sl = 0; sl < n_slices; ++sl) s += s_df[sl * a.rg_warps + wg][gg * (L * kV) + c];
+      for (int sl = 0; sl < a.slices; ++sl) s += s_df[sl * a.rg_warps + wg][gg * (L * kV) + c];
       const size_t o = (size_t)bn * a.dfeat_bs + (size_t)c * HW + (size_t)hh * a.fW + w;
       if (!kGeneral) reinterpret_cast<float*>(a.dfeat)[o] = s;
       else store_from_float(a.dfeat, o, s, a.out_dtype);
@@ -730,7 +746,8 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
     // softmax backward (reference: autograd of x.softmax(dim=1), src/modules.py:77), fused:
     // d_logit[d] = p[d] * (d_depth[d] - sum_d' p[d'] * d_depth[d']); one warp per pixel row
     const int rows = a.rg_warps * G;
-    for (int r = warp; r < rows; r += kBwdWarps) {
+    const int n_warps = blockDim.x >> 5;
+    for (int r = warp; r < rows; r += n_warps) {
       const int hh = rb * rows + r;
       if (hh >= a.fH) continue;
       const size_t pix = (size_t)hh * a.fW + w;

@@ -124,6 +124,19 @@ class GridSpec:
         return self.nx[0] * self.nx[1] * self.nx[2] * B
 
 
+def make_frustum(final_dim, downsample: int, dbound) -> torch.Tensor:
+    """The (D, fH, fW, 3) table of (u, v, depth) the models keep as their ``frustum`` parameter: the same
+    torch calls as the reference's create_frustum (src/model_baseline.py:37-48), for callers that have no
+    model instance at hand (benchmarks, tests)."""
+    ogfH, ogfW = final_dim
+    fH, fW = ogfH // downsample, ogfW // downsample
+    ds = torch.arange(*dbound, dtype=torch.float).view(-1, 1, 1).expand(-1, fH, fW)
+    D = ds.shape[0]
+    xs = torch.linspace(0, ogfW - 1, fW, dtype=torch.float).view(1, 1, fW).expand(D, fH, fW)
+    ys = torch.linspace(0, ogfH - 1, fH, dtype=torch.float).view(1, fH, 1).expand(D, fH, fW)
+    return torch.stack((xs, ys, ds), -1)
+
+
 def frustum_axes(frustum: torch.Tensor):
     """(us[fW], vs[fH], ds[D]) from the module's (D,fH,fW,3) frustum parameter
     (reference src/model_baseline.py:41-47): the frustum is the outer product of
@@ -421,12 +434,23 @@ def _alloc_bev(plan: Plan, C: int, dev) -> torch.Tensor:
     return torch.empty((plan.B, X, Y, Z * C), dtype=torch.float32, device=dev)
 
 
+# how often an upstream gradient arrived in another layout than channels_last and had to be transposed
+# (82 MB at the headline config: as much traffic as the backward itself).  A consumer that runs in
+# channels_last -- cuDNN does as soon as its input is, e.g. bevencode.conv1 (reference src/modules.py:99)
+# fed with our output -- hands the gradient back in that layout and this stays 0 (tests assert it).
+NHWC_TRANSPOSES = 0
+
+
 def _as_nhwc(grad: torch.Tensor) -> torch.Tensor:
     """View/copy of a logical (B, C, X, Y) tensor as contiguous (B, X, Y, C)."""
+    global NHWC_TRANSPOSES
     g = grad.permute(0, 2, 3, 1)
     if g.dtype != torch.float32:
         g = g.float()
-    return g if g.is_contiguous() else g.contiguous()
+    if not g.is_contiguous():
+        NHWC_TRANSPOSES += 1
+        g = g.contiguous()
+    return g
 
 
 # --------------------------------------------------------------------------
@@ -479,10 +503,9 @@ class _LiftSplat(torch.autograd.Function):
             raise RuntimeError("depth %s / feat %s do not match the plan (B=%d N=%d D=%d fH=%d fW=%d)"
                                % (tuple(depth.shape), tuple(feat.shape), plan.B, plan.N, plan.D,
                                   plan.fH, plan.fW))
+        # depth and feat may differ in dtype (under autocast the softmax output is float32, the conv
+        # output half: train_vovnet_transformer.py:196): each is read in its own type, no promotion copy
         ctx.in_dtypes = (depth.dtype, feat.dtype)
-        if depth.dtype != feat.dtype:
-            common = torch.promote_types(depth.dtype, feat.dtype)
-            depth, feat = depth.to(common), feat.to(common)
         depth_in = _feature_input(depth.detach())          # read in place: indexed by point id
         feat_t = feat_stage(feat.detach(), plan)
         bev = _fwd(dev, depth_in, feat_t, plan, C)

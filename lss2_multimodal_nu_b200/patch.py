@@ -19,6 +19,7 @@ unmodified script.
 from __future__ import annotations
 
 import types
+import weakref
 from typing import Optional
 
 import torch
@@ -28,6 +29,49 @@ from .lazy import LiftedFrustum
 
 _CACHE_ATTR = "_lss_b200_cache"  # plain python attribute: not in state_dict
 STATIC_BY_DEFAULT = False         # run.py sets it from LSS_STATIC_CALIB (evaluation with a fixed rig)
+PREFETCH_PLAN = True              # build the plan on a side stream as soon as model(...) is called
+
+
+# --------------------------------------------------------------------------
+# where a geometry tensor came from
+# --------------------------------------------------------------------------
+class _CalibRecord:
+    """The calibration tensors a geometry tensor was computed from, with the versions all of them had
+    at that moment.  voxel_pooling only trusts the record while the geometry tensor and every
+    calibration tensor are unmodified (torch bumps ``_version`` on every in-place write) and the
+    storage is the same; otherwise it quantises the tensor it was given, as the reference does."""
+
+    __slots__ = ("calib", "versions", "ptrs", "geom_version", "geom_ptr")
+
+    def __init__(self, geom: torch.Tensor, calib):
+        self.calib = tuple(calib)
+        self.versions = tuple(t._version for t in self.calib)
+        self.ptrs = tuple(t.data_ptr() for t in self.calib)
+        self.geom_version = geom._version
+        self.geom_ptr = geom.data_ptr()
+
+    def valid_for(self, geom: torch.Tensor) -> bool:
+        return (geom._version == self.geom_version and geom.data_ptr() == self.geom_ptr and
+                all(t._version == v and t.data_ptr() == p for t, v, p in zip(self.calib, self.versions, self.ptrs)))
+
+
+# id(geometry tensor) -> (weak reference to it, _CalibRecord).  The entry dies with the tensor (weakref
+# callback) and nothing hangs on the tensor itself: an attribute would survive `geom += offset` and travel
+# with copies of the python object.  (A WeakKeyDictionary cannot hold tensors: key comparison calls ==.)
+_GEOM_CALIB = {}
+
+
+def _remember_calib(geom: torch.Tensor, calib) -> None:
+    key = id(geom)
+    _GEOM_CALIB[key] = (weakref.ref(geom, lambda _r, k=key: _GEOM_CALIB.pop(k, None)), _CalibRecord(geom, calib))
+
+
+def _calib_of(geom) -> Optional[tuple]:
+    entry = _GEOM_CALIB.get(id(geom))
+    if entry is None or entry[0]() is not geom:
+        return None
+    rec = entry[1]
+    return rec.calib if rec.valid_for(geom) else None
 
 
 # --------------------------------------------------------------------------
@@ -44,6 +88,10 @@ class _ModuleCache:
         self.plan_builds = 0
         # producer fusion: None = not probed yet
         self.fuse_softmax: Optional[bool] = None
+        # plan built ahead on a side stream by the model's forward pre-hook: (calib key, plan, event)
+        self.prefetched = None
+        self.side_stream: Optional[torch.cuda.Stream] = None
+        self.prefetch_hits = 0
 
 
 def _cache(module) -> _ModuleCache:
@@ -77,17 +125,79 @@ def invalidate_plan(module) -> None:
     _cache(module).plan = None
 
 
+def _calib_key(calib):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in calib)
+
+
 def _plan_for(c: _ModuleCache, calib) -> F.Plan:
     if c.static and c.plan is not None:
         rots = calib[0]
         if (c.plan.B, c.plan.N) == (rots.shape[0], rots.shape[1]) and c.plan.cells.device == rots.device:
             return c.plan
+    pre = c.prefetched
+    if pre is not None:
+        c.prefetched = None
+        key, plan, event = pre
+        if key == _calib_key(calib):
+            # built on the side stream while the image backbone ran: order the consumer behind it and tell
+            # the allocator the tables are now used on this stream
+            cur = torch.cuda.current_stream(plan.cells.device)
+            cur.wait_event(event)
+            for t in (plan.cells, plan.key_start, plan.sorted_rec, plan.counts):
+                t.record_stream(cur)
+            c.prefetch_hits += 1
+            if c.static:
+                c.plan = plan
+            return plan
     us, vs, ds = c.axes
     plan = F.build_plan(us, vs, ds, *calib, c.grid)
     c.plan_builds += 1
     if c.static:
         c.plan = plan
     return plan
+
+
+def _looks_like_calibration(args) -> bool:
+    """model(imgs, rots, trans, intrins, post_rots, post_trans) -- reference src/model_baseline.py:135."""
+    if len(args) != 6 or not all(isinstance(t, torch.Tensor) for t in args):
+        return False
+    _, rots, trans, intrins, post_rots, post_trans = args
+    if not (rots.is_cuda and rots.dim() == 4 and trans.dim() == 3):
+        return False
+    B, N = rots.shape[:2]
+    return (tuple(rots.shape) == (B, N, 3, 3) and tuple(intrins.shape) == (B, N, 3, 3) and
+            tuple(post_rots.shape) == (B, N, 3, 3) and tuple(trans.shape) == (B, N, 3) and
+            tuple(post_trans.shape) == (B, N, 3))
+
+
+def _prefetch_plan_hook(module, args):
+    """forward pre-hook of a patched model: the calibration is known before the image backbone runs and
+    the plan depends on nothing else, so it is built NOW on a side stream; get_voxels / voxel_pooling
+    join it (zero plan latency on the model's stream)."""
+    if not PREFETCH_PLAN or not _looks_like_calibration(args):
+        return None
+    try:
+        c = _cache(module)
+    except AttributeError:
+        return None
+    if c.static and c.plan is not None:
+        return None
+    calib = tuple(args[1:])
+    dev = calib[0].device
+    if torch.cuda.is_current_stream_capturing():
+        return None
+    if c.side_stream is None or c.side_stream.device != dev:
+        c.side_stream = torch.cuda.Stream(dev)
+    side = c.side_stream
+    side.wait_stream(torch.cuda.current_stream(dev))        # the calibration tensors are ready there
+    us, vs, ds = c.axes
+    with torch.cuda.stream(side):
+        plan = F.build_plan(us, vs, ds, *calib, c.grid)
+        event = torch.cuda.Event()
+        event.record(side)
+    c.plan_builds += 1
+    c.prefetched = (_calib_key(calib), plan, event)
+    return None
 
 
 def _channels(module) -> int:
@@ -106,7 +216,7 @@ def get_geometry(self, rots, trans, intrins, post_rots, post_trans):
     out = F.geometry(us, vs, ds, rots, trans, intrins, post_rots, post_trans, c.grid, want_geom=True)
     geom = out["geom"]
     # remember where this tensor came from so voxel_pooling can skip re-quantising it
-    geom._lss_calib = (rots, trans, intrins, post_rots, post_trans)
+    _remember_calib(geom, (rots, trans, intrins, post_rots, post_trans))
     return geom
 
 
@@ -147,10 +257,12 @@ def get_cam_feats(self, x):
 def voxel_pooling(self, geom_feats, x):
     """(B, C*Z, X, Y) BEV; reference src/model_baseline.py:84-126."""
     c = _cache(self)
-    calib = getattr(geom_feats, "_lss_calib", None)
+    calib = _calib_of(geom_feats)
     if calib is not None:
         plan = _plan_for(c, calib)
     else:
+        # a geometry tensor from somewhere else, or edited since get_geometry made it: quantise what we
+        # were given, exactly as the reference does (src/model_baseline.py:92)
         plan = F.plan_from_geom(geom_feats, c.grid)
     if isinstance(x, LiftedFrustum):
         if not x.is_pooling_layout():
@@ -193,6 +305,14 @@ def _cam_encode_v2_forward(self, features, depth):
 # --------------------------------------------------------------------------
 _METHODS = {"get_geometry": get_geometry, "get_cam_feats": get_cam_feats,
             "voxel_pooling": voxel_pooling, "get_voxels": get_voxels}
+_INSTALLED_ATTR = "_lss_b200_installed"
+
+
+def has_lss_surface(module) -> bool:
+    """The attribute surface every lift-splat model of the reference exposes:
+    frustum / dx / bx / nx parameters and a voxel_pooling method."""
+    return (all(isinstance(getattr(module, a, None), torch.Tensor) for a in ("frustum", "dx", "bx", "nx")) and
+            callable(getattr(module, "voxel_pooling", None)) and callable(getattr(module, "get_geometry", None)))
 
 
 def install(target):
@@ -209,12 +329,45 @@ def install(target):
         ce = getattr(target, "cam_encode", None)
         if ce is not None and hasattr(ce, "feat_proj"):
             object.__setattr__(ce, "forward", types.MethodType(_cam_encode_v2_forward, ce))
+        if not target.__dict__.get(_INSTALLED_ATTR):
+            target.register_forward_pre_hook(_prefetch_plan_hook)
+            object.__setattr__(target, _INSTALLED_ATTR, True)
     return target
 
 
+def _install_on_first_forward(module, args):
+    """Global forward pre-hook (install_everywhere): the first time a module with the lift-splat surface
+    is called it gets the instance patch.  This reaches classes the class-level patch cannot see --
+    `PreTrainingModel` lives in the script that runs as __main__ (pre_train_vovnet.py:29-124) -- and any
+    user subclass."""
+    if module.__dict__.get(_INSTALLED_ATTR) or not has_lss_surface(module):
+        return None
+    install(module)
+    _prefetch_plan_hook(module, args)       # the instance hook was registered too late for this very call
+    return None
+
+
+_GLOBAL_HOOK = None
+
+
+def install_everywhere() -> None:
+    """Patch every lift-splat model at its first forward call, whatever class it is."""
+    global _GLOBAL_HOOK
+    if _GLOBAL_HOOK is None:
+        _GLOBAL_HOOK = torch.nn.modules.module.register_module_forward_pre_hook(_install_on_first_forward)
+
+
+def uninstall_everywhere() -> None:
+    global _GLOBAL_HOOK
+    if _GLOBAL_HOOK is not None:
+        _GLOBAL_HOOK.remove()
+        _GLOBAL_HOOK = None
+
+
 def install_reference_classes() -> int:
-    """Patch every hot-path class of the reference that is importable (``src`` on
-    sys.path).  Returns how many classes were patched."""
+    """Patch every hot-path class of the reference that is importable (``src`` on sys.path).  Returns how
+    many classes were patched.  Model classes defined elsewhere (``PreTrainingModel`` in
+    pre_train_vovnet.py, which runs as __main__) are reached by install_everywhere()."""
     import importlib
     n = 0
     for mod, classes in (("src.model_baseline", ("LSS", "BEV_TXT")),
