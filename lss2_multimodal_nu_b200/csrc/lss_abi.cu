@@ -161,10 +161,10 @@ static int launch_pool_fwd(const PoolFwdArgs& a0, int blocks, cudaStream_t st) {
 }
 
 #ifndef LSS_BWD_WIDE
-#define LSS_BWD_WIDE 1      // 1: C = 64 / 128 use 16-lane walkers (fewer registers, more warps in flight)
+#define LSS_BWD_WIDE 0      // 1: C = 64 / 128 use 16-lane walkers (fewer registers, more warps in flight; measured slower)
 #endif
 #ifndef LSS_BWD_BINS
-#define LSS_BWD_BINS 20     // depth bins a warp should at least own (slices of D)
+#define LSS_BWD_BINS 41     // depth bins a warp should at least own (slices of D)
 #endif
 
 static int launch_bwd(const PoolBwdArgs& a0, cudaStream_t st) {

@@ -187,7 +187,7 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // overwrites) and pdl_trigger() right after, which lets ITS successor be scheduled once all of its own
 // blocks have started.  Without the attribute both are no-ops.
 #ifndef LSS_PDL
-#define LSS_PDL 0
+#define LSS_PDL 5
 #endif
 __device__ __forceinline__ void pdl_wait() {
 #if LSS_PDL
@@ -212,27 +212,5 @@ inline cudaError_t launch_chain(int which, void (*kernel)(KArgs...), dim3 grid, 
   cfg.numAttrs = (LSS_PDL & which) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
-
-// Optional phase timestamps (build with -DLSS_PHASE_TIMING; tools/phase_timing.py reads them).
-#ifdef LSS_PHASE_TIMING
-__device__ unsigned long long g_phase_ts[3][4096 * 16];
-__device__ __forceinline__ void phase_stamp_any(int kernel, int slot) {   // caller picks the thread
-  if (blockIdx.x < 4096) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_phase_ts[kernel][blockIdx.x * 16 + slot] = t;
-  }
-}
-__device__ __forceinline__ void phase_stamp(int kernel, int slot) {
-  if (threadIdx.x == 0 && blockIdx.x < 4096) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_phase_ts[kernel][blockIdx.x * 16 + slot] = t;
-  }
-}
-#else
-__device__ __forceinline__ void phase_stamp_any(int, int) {}
-__device__ __forceinline__ void phase_stamp(int, int) {}
-#endif
 
 }  // namespace lss

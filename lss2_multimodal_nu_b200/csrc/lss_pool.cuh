@@ -194,6 +194,9 @@ constexpr int kZeroBytes = 2048;  // zero block in shared memory: source of the 
 #ifndef LSS_BWD_MINB
 #define LSS_BWD_MINB 2
 #endif
+#ifndef LSS_BWD_F2F_MIX
+#define LSS_BWD_F2F_MIX 1
+#endif
 
 __device__ __forceinline__ void f4_fma(float d, const float4& f, float4& a) {
   a.x = fmaf(d, f.x, a.x); a.y = fmaf(d, f.y, a.y); a.z = fmaf(d, f.z, a.z); a.w = fmaf(d, f.w, a.w);
@@ -613,6 +616,10 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
 #pragma unroll
       for (int v = 0; v < kV; ++v) fd[v] = 0.0;
     }
+    if (LSS_BWD_F2F_MIX) {
+#pragma unroll
+      for (int p = 0; p < kNP; ++p) { fd[4 * p + 1] *= 1.8928834978668395e-270; fd[4 * p + 3] *= 1.8928834978668395e-270; }   // 2^-896
+    }
   }
   float acc[kV];
 #pragma unroll
@@ -658,7 +665,10 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
         const float gv[4] = {gq[u][p].x, gq[u][p].y, gq[u][p].z, gq[u][p].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          s = fma(f32_as_scaled_f64(gv[k]), fd[4 * p + k], s);
+          // LSS_BWD_F2F_MIX: every other channel goes through the conversion instruction instead (its
+          // multiplicand carries the 2^-896), which takes work off the integer pipe
+          const double gd = (LSS_BWD_F2F_MIX && (k & 1)) ? static_cast<double>(gv[k]) : f32_as_scaled_f64(gv[k]);
+          s = fma(gd, fd[4 * p + k], s);
           acc[4 * p + k] = fmaf(dv[u], gv[k], acc[4 * p + k]);
         }
       }

@@ -36,8 +36,31 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(device) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (the raw getter is ~10x cheaper than building a
+    torch.cuda.Stream object; the eager module path asks a dozen times per step)."""
+    if _raw_stream is not None and device.index is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _device_guard(dev):
+    """torch.cuda.device(dev) only when dev is not already the current device."""
+    return _NO_GUARD if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
 
 
 def _call(dev, name: str, *args) -> None:
@@ -88,9 +111,39 @@ def _feature_input(t: torch.Tensor) -> torch.Tensor:
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     """float32 + contiguous (no copy when already so)."""
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+# ctypes structs and size queries are pure functions of small tuples: built once (the eager module path
+# issues a dozen C calls per step; their Python-side preparation is what bounds it)
+_GRID_C: Dict[Tuple, "_abi.LssGrid"] = {}
+_SHAPE_C: Dict[Tuple, "_abi.LssShape"] = {}
+_PLAN_SIZES: Dict[Tuple, Tuple[int, int, int]] = {}
+
+
+def _shape_c(B, N, D, fH, fW, C) -> "_abi.LssShape":
+    key = (B, N, D, fH, fW, C)
+    s = _SHAPE_C.get(key)
+    if s is None:
+        s = _SHAPE_C[key] = _abi.make_shape(*key)
+    return s
+
+
+def _plan_sizes(grid: "GridSpec", B, N, D, fH, fW) -> Tuple[int, int, int]:
+    """(workspace bytes, control bytes, n_keys) of a plan."""
+    key = (grid.dx, grid.bx, grid.nx, B, N, D, fH, fW)
+    v = _PLAN_SIZES.get(key)
+    if v is None:
+        lib = _abi.load()
+        shape, g = _shape_c(B, N, D, fH, fW, 4), grid.c()
+        v = _PLAN_SIZES[key] = (int(lib.lss_plan_workspace_bytes(shape, g)),
+                                int(lib.lss_plan_workspace_control_bytes(shape, g)),
+                                int(lib.lss_plan_key_count(g, B)))
+    return v
 
 
 @dataclass(frozen=True)
@@ -118,7 +171,11 @@ class GridSpec:
                         tuple(int(v) for v in nx.detach().cpu().tolist()))
 
     def c(self) -> _abi.LssGrid:
-        return _abi.make_grid(self.dx, self.bx, self.nx)
+        key = (self.dx, self.bx, self.nx)
+        g = _GRID_C.get(key)
+        if g is None:
+            g = _GRID_C[key] = _abi.make_grid(self.dx, self.bx, self.nx)
+        return g
 
     def n_cells(self, B: int) -> int:
         return self.nx[0] * self.nx[1] * self.nx[2] * B
@@ -276,7 +333,7 @@ class Plan:
         return self.sorted_rec[:, 0]
 
     def shape(self, C: int) -> _abi.LssShape:
-        return _abi.make_shape(self.B, self.N, self.D, self.fH, self.fW, C)
+        return _shape_c(self.B, self.N, self.D, self.fH, self.fW, C)
 
     def keys_of_cells(self, cells: torch.Tensor) -> torch.Tensor:
         """Tile-major sort key of output cells ((b*X + x)*Y + y)*Z + z (int64 tensor in, int64 out)."""
@@ -313,7 +370,7 @@ def keys_of_cells(cells, grid: GridSpec):
 
 
 def n_keys(grid: GridSpec, B: int) -> int:
-    return int(_abi.load().lss_plan_key_count(grid.c(), B))
+    return int(_abi.load().lss_plan_key_count(grid.c(), B))     # (cached per plan shape in _plan_sizes)
 
 
 class _Workspace:
@@ -379,19 +436,17 @@ def build_plan(us, vs, ds, rots, trans, intrins, post_rots, post_trans, grid: Gr
     dev = _need_cuda(us, vs, ds, rots, trans, intrins, post_rots, post_trans)
     B, N = trans.shape[0], trans.shape[1]
     D, fH, fW = ds.numel(), vs.numel(), us.numel()
-    shape = _abi.make_shape(B, N, D, fH, fW, 4)
-    g = grid.c()
+    nbytes, control, nkeys = _plan_sizes(grid, B, N, D, fH, fW)
     P = B * N * D * fH * fW
-    lib = _abi.load()
-    with torch.cuda.device(dev):
-        ws = _workspace(dev, lib.lss_plan_workspace_bytes(shape, g), lib.lss_plan_workspace_control_bytes(shape, g))
+    with _device_guard(dev):
+        ws = _workspace(dev, nbytes, control)
         buf = ws.acquire(dev)
-        cells, key_start, sorted_rec, counts = _plan_outputs(P, n_keys(grid, B), dev)
+        cells, key_start, sorted_rec, counts = _plan_outputs(P, nkeys, dev)
         try:
             _abi.call("lss_build_plan", _ptr(_f32c(us)), _ptr(_f32c(vs)), _ptr(_f32c(ds)),
                       _ptr(_f32c(rots)), _ptr(_f32c(trans)), _ptr(_f32c(intrins)),
-                      _ptr(_f32c(post_rots)), _ptr(_f32c(post_trans)), g, shape, _ptr(cells),
-                      _ptr(key_start), _ptr(sorted_rec), _ptr(counts), _ptr(buf), buf.numel(), _stream(dev))
+                      _ptr(_f32c(post_rots)), _ptr(_f32c(post_trans)), grid.c(), _shape_c(B, N, D, fH, fW, 4),
+                      _ptr(cells), _ptr(key_start), _ptr(sorted_rec), _ptr(counts), _ptr(buf), nbytes, _stream(dev))
         except _abi.LssError:
             ws.reset()  # a failed call may leave the control words dirty
             raise

@@ -52,7 +52,8 @@ class LiftSplatStep:
             self._allocate(us, vs, ds)
         self._side = torch.cuda.Stream(dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
-        self.kernels_per_step = 3 + 1 + 1 + 1      # plan (cells, scan, scatter+order), feature staging, fwd, bwd
+        self._graph_cached: Optional[torch.cuda.CUDAGraph] = None
+        self.kernels_per_step = 4 + 1 + 1 + 1      # plan (cells, scan, scatter, order), feature staging, fwd, bwd
         # warm run outside capture (module load, function attributes), then capture
         with torch.cuda.device(dev):
             with torch.cuda.stream(self._stream):
@@ -148,21 +149,45 @@ class LiftSplatStep:
                   p(self.feat_t), p(self.cells), self._g, self._shape, 0, _abi.LSS_F32, p(self.ddepth), self.D * HW,
                   p(self.dfeat), self.C * HW, st)
 
-    def _enqueue(self, main: torch.cuda.Stream, side: torch.cuda.Stream) -> None:
-        side.wait_stream(main)                      # fork: staging depends only on the features
-        self.enqueue_stage(side.cuda_stream)
-        self.enqueue_plan(main.cuda_stream)         # the plan depends only on the calibration
-        main.wait_stream(side)                      # join
+    def _enqueue(self, main: torch.cuda.Stream, side: torch.cuda.Stream, with_plan: bool = True) -> None:
+        if with_plan:
+            side.wait_stream(main)                  # fork: staging depends only on the features
+            self.enqueue_stage(side.cuda_stream)
+            self.enqueue_plan(main.cuda_stream)     # the plan depends only on the calibration
+            main.wait_stream(side)                  # join
+        else:
+            self.enqueue_stage(main.cuda_stream)
         self.enqueue_fwd(main.cuda_stream)
         self.enqueue_bwd(main.cuda_stream)
 
-    def run(self) -> None:
-        """Enqueue one forward + backward on ``self.stream`` (graph replay when captured)."""
+    def run(self, wait_current: bool = False) -> None:
+        """Enqueue one forward + backward on ``self.stream`` (graph replay when captured).
+        ``wait_current``: order the step behind the caller's current stream first (inputs or the
+        upstream gradient were written there)."""
+        with torch.cuda.device(self.dev):
+            if wait_current:
+                self._stream.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(self._stream):
+                if self._graph is not None:
+                    self._graph.replay()
+                else:
+                    self._enqueue(self._stream, self._side)
+
+    def run_cached_plan(self) -> None:
+        """The same step with the plan of the LAST run() reused: feature staging + forward + backward only.
+        This is evaluation with a fixed camera rig (patch.static_calibration): the index
+        tables depend on the calibration alone."""
         with torch.cuda.device(self.dev), torch.cuda.stream(self._stream):
-            if self._graph is not None:
-                self._graph.replay()
-            else:
-                self._enqueue(self._stream, self._side)
+            if self._graph is None:
+                self._enqueue(self._stream, self._side, with_plan=False)
+                return
+            if self._graph_cached is None:
+                self._enqueue(self._stream, self._side, with_plan=False)      # warm
+                self._stream.synchronize()
+                self._graph_cached = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph_cached, stream=self._stream):
+                    self._enqueue(torch.cuda.current_stream(self.dev), self._side, with_plan=False)
+            self._graph_cached.replay()
 
     def load(self, tensors: Dict[str, torch.Tensor]) -> None:
         """Copy device or host tensors into the step's input buffers (on ``self.stream``)."""

@@ -52,6 +52,16 @@ def sum_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def gather_floats(value: float, device=None):
+    """Every rank's scalar, as a list ordered by rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(value)]
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
 def aggregate_throughput(samples_this_rank: int, elapsed_ms_this_rank: float, device=None) -> float:
     """Whole-job samples/s: all ranks' samples over the slowest rank's time."""
     total = sum_over_ranks(samples_this_rank, device)

@@ -202,6 +202,40 @@ def make_dbev(cfg: LSSConfig, seed: int = 1234) -> np.ndarray:
     return rs.standard_normal((cfg.B, cfg.C * nx[2], nx[0], nx[1])).astype(np.float32)
 
 
+# --------------------------------------------------------------------------
+# a cheap deterministic field for the multi-GB upstream gradients of the large configurations: its value
+# at any logical index can be evaluated on its own (fixtures sample it with numpy, the GPU tests fill the
+# whole tensor with torch), bit-identical on both sides: 24 hashed bits scaled to [-0.5, 0.5).
+# --------------------------------------------------------------------------
+_HASH_MUL = 2654435761
+
+
+def hash_field_np(idx, seed: int = 1234) -> np.ndarray:
+    v = ((np.asarray(idx, dtype=np.int64) * _HASH_MUL + seed * 40503) & 0xFFFFFFFF) >> 8
+    return (v.astype(np.float32) * np.float32(2.0 ** -24) - np.float32(0.5)).astype(np.float32)
+
+
+def hash_field_torch(idx, seed: int = 1234):
+    import torch
+    v = ((idx.to(torch.int64) * _HASH_MUL + seed * 40503) & 0xFFFFFFFF) >> 8
+    return v.to(torch.float32) * (2.0 ** -24) - 0.5
+
+
+def hash_dbev_nhwc(cfg: "LSSConfig", device, seed: int = 1234):
+    """The (B, X, Y, Z*C) channels-innermost storage of the logical (B, C*Z, X, Y) gradient whose element
+    [b, ch, x, y] is hash_field(((b*CZ + ch)*X + x)*Y + y)."""
+    import torch
+    X, Y, Z = cfg.nx
+    CZ = cfg.C * Z
+    out = torch.empty((cfg.B, X, Y, CZ), dtype=torch.float32, device=device)
+    ch = torch.arange(CZ, device=device, dtype=torch.int64).view(1, 1, CZ) * (X * Y)
+    xy = (torch.arange(X, device=device, dtype=torch.int64).view(X, 1, 1) * Y +
+          torch.arange(Y, device=device, dtype=torch.int64).view(1, Y, 1))
+    for b in range(cfg.B):                       # one sample at a time keeps the int64 temporaries small
+        out[b] = hash_field_torch(b * CZ * X * Y + ch + xy, seed)
+    return out
+
+
 def to_torch(d: Dict[str, np.ndarray], device="cpu"):
     import torch
     return {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in d.items()}

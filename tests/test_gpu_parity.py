@@ -370,6 +370,59 @@ def test_large_shapes_against_oracle(cname, B):
     close(cpu(feat.grad), df)
 
 
+@pytest.mark.parametrize("cname", ["config4", "config5"])
+def test_large_configs_full_size_digests(golden_dir, cname):
+    """BASELINE.json configs 4 (B=16, 256x704, D=59, C=80) and 5 (B=32, D=118, C=128, 512x512) at their FULL
+    batch -- where the 32-bit offsets of the kernels are closest to their limits: every index tensor hashed
+    against the reference's own (oracle/make_golden.py --large), values at sampled outputs against float64."""
+    with open(os.path.join(golden_dir, cname + ".json")) as f:
+        g = json.load(f)
+    cfg = S.config(cname)
+    assert cfg.B == g["B"] and cfg.P == g["P"]
+    cal = S.make_calibration(cfg, 1234); ft = S.make_features(cfg, 1234)
+    assert "".join(sha(cal[k]) for k in sorted(cal)) == g["sha256"]["calibration"]
+    assert sha(ft["depth"]) + sha(ft["feat"]) == g["sha256"]["inputs"]
+    axes = F.frustum_axes(F.make_frustum(cfg.final_dim, cfg.downsample, cfg.dbound).to(DEV))
+    grid = F.GridSpec.from_bounds(cfg.xbound, cfg.ybound, cfg.zbound)
+    calib = [dev(cal[k]) for k in CAL]
+    ipr, comb = F.camera_prep(calib[0], calib[2], calib[3])
+    assert sha(cpu(ipr)) == g["sha256"]["inv_post_rots"] and sha(cpu(comb)) == g["sha256"]["combine"]
+    out = F.geometry(*axes, *calib, grid, want_geom=True, want_coords=True, want_kept=True)
+    assert sha(cpu(out["geom"])) == g["sha256"]["geom"]
+    assert sha(cpu(out["coords"])) == g["sha256"]["coords_i32"]
+    kept = cpu(out["kept"]).astype(bool)
+    assert sha(kept.astype(np.uint8)) == g["sha256"]["kept_u8"]
+    assert sha(cpu(out["ranks"])[kept]) == g["sha256"]["ranks_i32"]
+    del out["geom"], out["coords"]
+    plan = F.build_plan(*axes, *calib, grid)
+    K, V = cpu(plan.counts).tolist()
+    assert (K, V) == (g["K"], g["V"])
+    ref_order = cpu(plan.reference_order())
+    compact = np.cumsum(kept) - 1
+    assert sha(compact[ref_order].astype(np.int32)) == g["sha256"]["sorts_i32"]
+    check_plan_tables(plan, ref_order)
+    sk, _ = F.sort_ranks(out["ranks"], grid.n_cells(cfg.B))
+    _, _, last, _ = F.intervals(sk, grid, cfg.B, want_last_mask=True)
+    assert sha(cpu(last)[:K]) == g["sha256"]["last_mask_u8"]
+    del sk, last, out
+    depth = dev(ft["depth"]).requires_grad_(True); feat = dev(ft["feat"]).requires_grad_(True)
+    bev = F.lift_splat(depth, feat, plan)
+    pick = torch.tensor(g["bev_pick"], device=DEV, dtype=torch.long)
+    got = bev.detach()[pick[:, 0], pick[:, 1], pick[:, 2], pick[:, 3]]
+    close(cpu(got), np.array(g["bev64_at"]))
+    X, Y, Z = cfg.nx
+    assert int((bev.detach().reshape(cfg.B, -1) != 0).any(0).numel()) > 0
+    dbev = S.hash_dbev_nhwc(cfg, DEV).permute(0, 3, 1, 2)            # logical (B, C*Z, X, Y), channels_last strides
+    bev.backward(dbev)
+    close(cpu(depth.grad.reshape(-1)[torch.tensor(g["d_depth_pick"], device=DEV)]), np.array(g["d_depth64_at"]))
+    close(cpu(feat.grad.reshape(-1)[torch.tensor(g["d_feat_pick"], device=DEV)]), np.array(g["d_feat64_at"]))
+    # size-independent property at full size: per (sample, channel) mass of the map = sum over kept points
+    kept_t = (plan.cells >= 0).view(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW)
+    w = (depth.detach().view(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW) * kept_t).double().sum(2)
+    want = torch.einsum("bnhw,bnchw->bc", w, feat.detach().view(cfg.B, cfg.N, cfg.C, cfg.fH, cfg.fW).double())
+    close(cpu(bev.detach().double().sum(dim=(2, 3))), cpu(want), rtol=1e-6, atol=1e-5)
+
+
 def test_linearity_and_mass_conservation_full_size():
     """Size-independent properties at the headline shape."""
     cfg = S.config("config2")

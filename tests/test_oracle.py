@@ -166,3 +166,28 @@ def test_config2_digests(golden_dir):
     assert sha(ic["sorts"].astype(np.int32)) == g["sha256"]["sorts_i32"]
     b0, _, _, K, V = CO.step(ft["depth"], ft["feat"], geom, dbev, dx, bx, nx, cfg.B, cfg.N, mode=0, backward=False)
     assert (K, V) == (g["K"], g["V"]) and sha(b0) == g["sha256"]["bev32"]
+
+
+def test_oracle_reproduces_reference_digests_at_config4_full_size(golden_dir):
+    """The numpy restatement against the reference's own index tensors at BASELINE.json config 4, full batch
+    (B=16, 4 M points): geometry, truncated coordinates, kept mask, ranks, sort order, interval mask."""
+    import hashlib
+    import json
+    import os
+    from lss2_multimodal_nu_b200 import synthetic as S
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    with open(os.path.join(golden_dir, "config4.json")) as f:
+        g = json.load(f)
+    cfg = S.config("config4")
+    cal = S.make_calibration(cfg, 1234)
+    fr = O.create_frustum(cfg.final_dim, cfg.downsample, cfg.dbound)
+    dx, bx, nx = O.gen_dx_bx(cfg.xbound, cfg.ybound, cfg.zbound)
+    geom = O.get_geometry(fr, **cal)
+    assert sha(geom) == g["sha256"]["geom"]
+    ip = O.index_pipeline(geom, dx, bx, nx, cfg.B)
+    assert len(ip["ranks"]) == g["K"] and len(ip["interval_start"]) == g["V"]
+    assert sha(ip["ranks"].astype(np.int32)) == g["sha256"]["ranks_i32"]
+    assert sha(ip["sorts"].astype(np.int32)) == g["sha256"]["sorts_i32"]

@@ -2,13 +2,12 @@
 import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import lss_oracle as O
+sys.path.insert(0, ROOT)
 from lss2_multimodal_nu_b200 import functional as F, synthetic as S
 from lss2_multimodal_nu_b200.pipeline import HostPipeline, LiftSplatStep
 cfg = S.config("config2"); dev = torch.device("cuda:0")
 grid = F.GridSpec.from_bounds(cfg.xbound, cfg.ybound, cfg.zbound)
-us, vs, ds = (torch.from_numpy(a).to(dev) for a in O.frustum_axes(cfg.final_dim, cfg.downsample, cfg.dbound))
+us, vs, ds = F.frustum_axes(F.make_frustum(cfg.final_dim, cfg.downsample, cfg.dbound).to(dev))
 cal = S.make_calibration(cfg); ft = S.make_features(cfg)
 host = {k: torch.from_numpy(v).pin_memory() for k, v in {**cal, **ft}.items()}
 mk = lambda: LiftSplatStep(cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, cfg.C, grid, us, vs, ds, device=dev)

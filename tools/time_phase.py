@@ -37,6 +37,7 @@ def main():
         cal = S.make_calibration(cfg, 1234 + s); ft = S.make_features(cfg, 1234 + s)
         st.load({k: torch.from_numpy(v) for k, v in {**cal, **ft}.items()})
         st._dbev.normal_()
+        st.run()                       # every phase once, in order: later phases need the earlier ones' outputs
         steps.append(st)
     torch.cuda.synchronize()
     out = []
