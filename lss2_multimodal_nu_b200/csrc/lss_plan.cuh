@@ -21,8 +21,8 @@
 //               order a STABLE sort gives (argsort on torch's radix path): a
 //               slot finds its run by looking at its neighbours (equal cell) and
 //               counts the smaller ids -- no key arithmetic, no table lookups.
-//               Runs of more than 64 points (coarse grids, adversarial inputs) are
-//               ordered by the warp that holds their first slot.
+//               Runs that do not fit the neighbour window are ordered by (part of)
+//               the warp that holds their first slot.
 // The key is the OUTPUT CELL in tile-major order (KeyMap, lss_common.cuh): the
 // digits (b, x, y, z) of the reference's rank x*(Y*Z*B) + y*(Z*B) + z*B + b
 // regrouped as (b, x/8, y/8, x%8, y%8, z) -- a bijection of the rank, so runs,
@@ -42,8 +42,9 @@ constexpr int kPlanThreads = 256;
 constexpr int kScanBlock = kPlanThreads * 4;           // keys per scan step (one uint4 per thread)
 constexpr int kScanMaxTiles = 1024;                    // tile totals a scan CTA sums for its base
 constexpr int kTsumCopies = 8;                         // replicas of the tile totals (spreads the atomics of P1)
-constexpr int kRunSerial = 64;                         // runs up to this: every slot counts the smaller ids of its run
-constexpr int kRunWarp = 256;                          // ... up to this: by the warp of the run's first slot; longer: last CTA
+constexpr int kOrderWin = 4;                           // neighbours a slot loads up front on either side to find its run
+constexpr int kRunSerial = 128;                        // runs up to this: every slot counts the smaller ids of its run
+constexpr int kRunWarp = 1024;                         // longer runs up to this: sorted by a warp in shared memory
 
 struct PlanWorkspace {
   size_t off_cnt, off_tsum, off_ctl, off_keys, off_tmp, control_bytes, total_bytes;
@@ -401,54 +402,47 @@ plan_order_kernel(PlanOrderArgs a) {
     } else {
       const int ii = static_cast<int>(i);
       const int2 me = __ldg(a.tmp + ii);
-      // the run of this slot = the neighbours with the same cell; count the smaller ids on the way.
-      // The four neighbours on either side are loaded up front (independent loads, one round trip:
-      // most runs are that short); only longer runs continue with a dependent scan.
-      constexpr int kWin = 4;
-      int2 lw[kWin], rw[kWin];
+      // the run of this slot = the neighbours with the same cell; count the smaller ids on the way.  The
+      // kOrderWin neighbours on either side are loaded up front (independent loads, one round trip); a
+      // slot that sees both ends of its run among them has seen the whole run and is done.
+      int2 lw[kOrderWin], rw[kOrderWin];
 #pragma unroll
-      for (int k = 0; k < kWin; ++k) {
+      for (int k = 0; k < kOrderWin; ++k) {
         lw[k] = make_int2(-2, 0); rw[k] = make_int2(-2, 0);          // -2: no such slot (cells are >= 0)
         if (ii - 1 - k >= 0) lw[k] = __ldg(a.tmp + ii - 1 - k);
         if (ii + 1 + k < K) rw[k] = __ldg(a.tmp + ii + 1 + k);
       }
-      int rank = 0, left = 0, right = 0;
+      int rank = 0, left = 0;
       bool lgo = true, rgo = true;
 #pragma unroll
-      for (int k = 0; k < kWin; ++k) {
+      for (int k = 0; k < kOrderWin; ++k) {
         lgo = lgo && lw[k].x == me.x;
         rgo = rgo && rw[k].x == me.x;
         rank += (lgo && lw[k].y < me.y) ? 1 : 0;
         rank += (rgo && rw[k].y < me.y) ? 1 : 0;
         left += lgo ? 1 : 0;
-        right += rgo ? 1 : 0;
       }
-      if (lgo)
-        for (int j = ii - 1 - kWin; j >= 0 && left < kRunSerial; --j) {
-          const int2 o = __ldg(a.tmp + j);
-          if (o.x != me.x) break;
-          rank += (o.y < me.y) ? 1 : 0;
-          ++left;
-        }
-      if (rgo)
-        for (int j = ii + 1 + kWin; j < K && right < kRunSerial; ++j) {
-          const int2 o = __ldg(a.tmp + j);
-          if (o.x != me.x) break;
-          rank += (o.y < me.y) ? 1 : 0;
-          ++right;
-        }
-      if (left + right + 1 <= kRunSerial) {
-        a.rec[ii - left + rank] = me;
-      } else if (left == 0) {
-        // first slot of a long run (every slot of the run takes this branch or does nothing):
-        // its length comes from the interval table
+      if (!lgo && !rgo) {
+        a.rec[ii - left + rank] = me;                                  // the whole run was inside the window
+      } else {
+        // longer run: its bounds come from the interval table; up to kRunSerial points every slot counts
+        // the smaller ids itself (neighbouring lanes sit in the same run: same trip count, the loads are
+        // broadcasts out of L1), beyond that the warp of the run's first slot sorts it
         const uint32_t key = a.keys.key_of_cell(static_cast<uint32_t>(me.x));
-        pend_start = ii;
-        pend_n = __ldg(a.key_start + key + 1) - ii;
+        const int s0 = __ldg(a.key_start + key), e0 = __ldg(a.key_start + key + 1);
+        if (e0 - s0 <= kRunSerial) {
+          int r = 0;
+#pragma unroll 4
+          for (int j = s0; j < e0; ++j) r += (__ldg(&a.tmp[j].y) < me.y) ? 1 : 0;
+          a.rec[s0 + r] = me;
+        } else if (ii == s0) {
+          pend_start = s0;
+          pend_n = e0 - s0;
+        }
       }
     }
   }
-  // runs of more than kRunSerial points: the warp of the run's first slot orders them, one run at a time
+  // ---- runs of more than kRunSerial points, by the warp that holds their first slot, one at a time ----
   uint32_t pend = __ballot_sync(0xffffffffu, pend_n > 0);
   while (pend) {
     const int src = __ffs(pend) - 1;
@@ -456,26 +450,42 @@ plan_order_kernel(PlanOrderArgs a) {
     const int start = __shfl_sync(0xffffffffu, pend_start, src);
     const int n = __shfl_sync(0xffffffffu, pend_n, src);
     const int32_t cell = __ldg(&a.tmp[start].x);
+    int n2 = 32;
+    while (n2 < n) n2 <<= 1;
     __syncwarp();
+    // bitonic network whose compare-exchanges all point the same way (the +inf padding never has to
+    // move): in shared memory up to kRunWarp ids, in place in the output beyond (adversarial inputs:
+    // everything in a few voxels)
     if (n <= kRunWarp) {
-      // up to 256 points: ids into shared memory, every lane counts the smaller ones of its ids
-      for (int k = lane; k < n; k += 32) s_run[warp][k] = __ldg(&a.tmp[start + k].y);
+      int32_t* v = s_run[warp];
+      for (int k = lane; k < n2; k += 32) v[k] = (k < n) ? __ldg(&a.tmp[start + k].y) : 0x7fffffff;
       __syncwarp();
-      for (int k = lane; k < n; k += 32) {
-        const int32_t v = s_run[warp][k];
-        int r = 0;
-        for (int j = 0; j < n; ++j) r += (s_run[warp][j] < v) ? 1 : 0;
-        a.rec[start + r] = make_int2(cell, v);
+      for (int lk = 1; (1 << lk) <= n2; ++lk) {                 // k = 1 << lk
+        const int k = 1 << lk, half = k >> 1;
+        for (int t = lane; t < (n2 >> 1); t += 32) {
+          const int blk = t >> (lk - 1), r0 = t & (half - 1);
+          const int x = blk * k + r0, l = blk * k + (k - 1 - r0);
+          const int32_t p = v[x], q = v[l];
+          if (q < p) { v[x] = q; v[l] = p; }
+        }
+        __syncwarp();
+        for (int lj = lk - 2; lj >= 0; --lj) {                    // j = 1 << lj
+          const int j = 1 << lj;
+          for (int t = lane; t < (n2 >> 1); t += 32) {
+            const int blk = t >> lj, r0 = t & (j - 1);
+            const int x = blk * 2 * j + r0, l = x + j;
+            const int32_t p = v[x], q = v[l];
+            if (q < p) { v[x] = q; v[l] = p; }
+          }
+          __syncwarp();
+        }
       }
+      for (int k = lane; k < n; k += 32) a.rec[start + k] = make_int2(cell, v[k]);
     } else {
-      // longer (adversarial inputs: everything in a few voxels): bitonic network in place in the output,
-      // all compare-exchanges pointing the same way, so the virtual +inf padding never has to move
       volatile int2* v = a.rec + start;
       for (int k = lane; k < n; k += 32) { v[k].x = cell; v[k].y = a.tmp[start + k].y; }
       __threadfence_block();
       __syncwarp();
-      int n2 = 1;
-      while (n2 < n) n2 <<= 1;
       for (int k = 2; k <= n2; k <<= 1) {
         const int half = k >> 1;
         for (int t = lane; t < (n2 >> 1); t += 32) {
