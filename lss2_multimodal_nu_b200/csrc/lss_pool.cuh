@@ -569,7 +569,9 @@ struct PoolBwdArgs {
   int softmax;              // 1: depth = softmax(logits); emit d_logits = p * (d_depth - sum_d p * d_depth)
   int D, fH, fW, C, BN;
   int nact;                 // lanes of a walker that own channels
-  int rg_warps;             // warps of a CTA along the rows; the CTA's other warps slice D
+  int cols;                 // adjacent image columns per CTA (their rays cross the same voxels: L1 reuse)
+  int w_blocks;             // ceil(fW / cols)
+  int rg_warps;             // warps of a column along the rows; the column's other warps slice D
   int slices;               // depth slices (warps per row group)
   int d_per_slice;
   int row_blocks;           // CTAs per image column: ceil(fH / (G * rg_warps))
@@ -600,13 +602,17 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
   const int g = lane / L, sub = lane % L;
   pdl_wait();
   // CTA -> (image column, block of rows); warp -> (row group, depth slice)
-  const int col = blockIdx.x / a.row_blocks, rb = blockIdx.x - col * a.row_blocks;
-  const int bn = col / a.fW, w = col - bn * a.fW;
-  const int rg = warp % a.rg_warps, slice = warp / a.rg_warps;
+  const int colblk = blockIdx.x / a.row_blocks, rb = blockIdx.x - colblk * a.row_blocks;
+  const int bn = colblk / a.w_blocks;
+  const int wpc = a.rg_warps * a.slices;                     // warps per column
+  const int cw = warp / wpc, wl = warp - cw * wpc;
+  const int w = (colblk - bn * a.w_blocks) * a.cols + cw;
+  const int rg = wl % a.rg_warps, slice = wl / a.rg_warps;
   const int h = (rb * a.rg_warps + rg) * G + g;
-  const bool pix_ok = h < a.fH;
+  const bool pix_ok = h < a.fH && w < a.fW;
   const int HW = a.fH * a.fW;
-  const int hw = (pix_ok ? h : 0) * a.fW + w;
+  const int hw = pix_ok ? h * a.fW + w : 0;
+  const int crow = (cw * a.rg_warps + rg) * G + g;           // pixel of this walker among the CTA's pixels
   const int d_lo = slice * a.d_per_slice;
   const int d_hi = min(a.D, d_lo + a.d_per_slice);
   const bool lane_act = sub < a.nact;
@@ -745,7 +751,7 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
       if (wcell < 0) r = 0.f;
       const size_t o = (size_t)bn * a.ddepth_bs + (size_t)d * HW + hw;
       if (!kGeneral) reinterpret_cast<float*>(a.ddepth)[o] = r;
-      else if (a.softmax) s_dd[rg * G + g][d] = r;            // D <= kBwdMaxD (host)
+      else if (a.softmax) s_dd[crow][d] = r;                  // D <= kBwdMaxD (host)
       else store_from_float(a.ddepth, o, r, a.out_dtype);
     }
   }
@@ -762,7 +768,7 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
       for (int d = d_lo + sub; d < d_hi; d += L) {
         const size_t o = (size_t)bn * a.ddepth_bs + (size_t)d * HW + hw;
         if (!kGeneral) reinterpret_cast<float*>(a.ddepth)[o] = qnan;
-        else if (a.softmax) s_dd[rg * G + g][d] = qnan;
+        else if (a.softmax) s_dd[crow][d] = qnan;
         else store_from_float(a.ddepth, o, qnan, a.out_dtype);
       }
     }
@@ -778,39 +784,41 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
   __syncthreads();
   {
     const int rows = a.rg_warps * G;                         // pixel rows of this CTA
-    // consecutive threads -> consecutive rows (the contiguous direction of the output is w, which
-    // a column CTA does not span), channels outer
-    for (int i = threadIdx.x; i < rows * a.C; i += blockDim.x) {
-      const int r = i % rows, c = i / rows;
-      const int hh = rb * rows + r;
-      if (hh >= a.fH) continue;
+    // consecutive threads -> consecutive columns w (the contiguous direction of the output), then rows,
+    // channels outer
+    for (int i = threadIdx.x; i < a.cols * rows * a.C; i += blockDim.x) {
+      const int cc = i % a.cols, t = i / a.cols;
+      const int r = t % rows, c = t / rows;
+      const int hh = rb * rows + r, ww = (colblk - bn * a.w_blocks) * a.cols + cc;
+      if (hh >= a.fH || ww >= a.fW) continue;
       const int wg = r / G, gg = r - wg * G;                 // row group (warp along rows), walker
       float s = 0.f;
-      for (int sl = 0; sl < a.slices; ++sl) s += s_df[sl * a.rg_warps + wg][gg * (L * kV) + c];
-      const size_t o = (size_t)bn * a.dfeat_bs + (size_t)c * HW + (size_t)hh * a.fW + w;
+      for (int sl = 0; sl < a.slices; ++sl) s += s_df[(cc * a.slices + sl) * a.rg_warps + wg][gg * (L * kV) + c];
+      const size_t o = (size_t)bn * a.dfeat_bs + (size_t)c * HW + (size_t)hh * a.fW + ww;
       if (!kGeneral) reinterpret_cast<float*>(a.dfeat)[o] = s;
       else store_from_float(a.dfeat, o, s, a.out_dtype);
     }
   }
   if (kGeneral && a.softmax) {
     // softmax backward (reference: autograd of x.softmax(dim=1), src/modules.py:77), fused:
-    // d_logit[d] = p[d] * (d_depth[d] - sum_d' p[d'] * d_depth[d']); one warp per pixel row
+    // d_logit[d] = p[d] * (d_depth[d] - sum_d' p[d'] * d_depth[d']); one warp per pixel
     const int rows = a.rg_warps * G;
     const int n_warps = blockDim.x >> 5;
-    for (int r = warp; r < rows; r += n_warps) {
-      const int hh = rb * rows + r;
-      if (hh >= a.fH) continue;
-      const size_t pix = (size_t)hh * a.fW + w;
+    for (int q = warp; q < a.cols * rows; q += n_warps) {
+      const int cc = q / rows, r = q - cc * rows;
+      const int hh = rb * rows + r, ww = (colblk - bn * a.w_blocks) * a.cols + cc;
+      if (hh >= a.fH || ww >= a.fW) continue;
+      const size_t pix = (size_t)hh * a.fW + ww;
       double sp = 0.0;
       for (int d = lane; d < a.D; d += 32)
         sp += static_cast<double>(load_as_float(a.depth, (size_t)bn * a.depth_bs + (size_t)d * HW + pix, a.depth_dtype)) *
-              static_cast<double>(s_dd[r][d]);
+              static_cast<double>(s_dd[q][d]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
       const float spf = static_cast<float>(sp);
       for (int d = lane; d < a.D; d += 32) {
         const float pd = load_as_float(a.depth, (size_t)bn * a.depth_bs + (size_t)d * HW + pix, a.depth_dtype);
-        store_from_float(a.ddepth, (size_t)bn * a.ddepth_bs + (size_t)d * HW + pix, pd * (s_dd[r][d] - spf), a.out_dtype);
+        store_from_float(a.ddepth, (size_t)bn * a.ddepth_bs + (size_t)d * HW + pix, pd * (s_dd[q][d] - spf), a.out_dtype);
       }
     }
   }

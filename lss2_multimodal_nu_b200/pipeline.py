@@ -173,6 +173,23 @@ class LiftSplatStep:
                 else:
                     self._enqueue(self._stream, self._side)
 
+    def capture_repeated(self, n: int) -> "torch.cuda.CUDAGraph":
+        """ONE CUDA graph holding ``n`` whole steps back to back on this step's stream (the launch sequence
+        of run(), n times).  A driver that issues many steps per host call is no longer paced by the host's
+        graph-launch rate (one launch per ~50 us step per stream otherwise)."""
+        with torch.cuda.device(self.dev):
+            self._stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                cur = torch.cuda.current_stream(self.dev)
+                for _ in range(n):
+                    self._enqueue(cur, self._side)
+        return g
+
+    def replay(self, graph) -> None:
+        with torch.cuda.device(self.dev), torch.cuda.stream(self._stream):
+            graph.replay()
+
     def run_cached_plan(self) -> None:
         """The same step with the plan of the LAST run() reused: feature staging + forward + backward only.
         This is evaluation with a fixed camera rig (patch.static_calibration): the index
