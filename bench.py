@@ -511,7 +511,7 @@ def run_ours(args, cfg):
             out = pipe.collect()
             checksum += float(out["d_depth"][0, 0, 0, 0])
 
-    e2e_run(40)
+    e2e_run(max(1000, 2 * e2e_steps))      # warm the host side too: the first few hundred steps of a fresh process run at half speed
     # the host link this number is bound by: pinned copies of a step's blocks, ALL ranks at once -- H2D alone,
     # then H2D and D2H together on two streams (what the pipeline does)
     blk = host_blocks[0]; st0 = pipe.slots[0]["step"]; dst = st0.in_block
@@ -535,7 +535,7 @@ def run_ours(args, cfg):
     link_all = shard.gather_floats(link_gbs, dev) if world > 1 else [link_gbs]
     bidir_all = shard.gather_floats(bidir_gbs, dev) if world > 1 else [bidir_gbs]
     reps = []
-    for _ in range(5):                        # host wall clock is noisy: median of five runs of e2e_steps
+    for _ in range(9):                        # host wall clock is noisy: median of nine runs of e2e_steps
         barrier()
         t0 = time.perf_counter()
         e2e_run(e2e_steps)
