@@ -165,3 +165,78 @@ def test_synthetic_inputs_are_deterministic_and_shaped():
     alg = cfg.algorithmic_bytes()
     assert alg["fwd"] == 85468160 and alg["bwd"] == 89016320 and alg["total"] == 174484480
     assert S.config("config4").algorithmic_bytes()["total"] == 522330112
+
+
+def test_geometry_provenance_records_follow_versions():
+    """patch remembers which calibration a geometry tensor came from only while neither was modified."""
+    import gc
+    import torch
+    from lss2_multimodal_nu_b200 import patch
+    g = torch.zeros(2, 3)
+    cal = tuple(torch.ones(2) for _ in range(5))
+    patch._remember_calib(g, cal)
+    assert patch._calib_of(g) == cal
+    assert patch._calib_of(g.clone()) is None               # another tensor, however equal
+    g += 1                                                   # in-place edit: quantise what you are given
+    assert patch._calib_of(g) is None
+    patch._remember_calib(g, cal)
+    cal[3].mul_(2)                                           # calibration edited after get_geometry
+    assert patch._calib_of(g) is None
+    n = len(patch._GEOM_CALIB)
+    del g
+    gc.collect()
+    assert len(patch._GEOM_CALIB) == n - 1                   # the record dies with the tensor
+
+
+def test_install_everywhere_patches_script_defined_models_at_first_forward():
+    """A model class the class-level patch cannot know (the reference's PreTrainingModel lives in the script
+    run as __main__) is patched by the global forward pre-hook the first time it is called."""
+    import torch
+    from lss2_multimodal_nu_b200 import patch
+
+    class ScriptModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            for n, shape in (("frustum", (4, 2, 3, 3)), ("dx", (3,)), ("bx", (3,))):
+                setattr(self, n, torch.nn.Parameter(torch.ones(shape), requires_grad=False))
+            self.nx = torch.nn.Parameter(torch.tensor([8, 8, 1]), requires_grad=False)
+
+        def get_geometry(self, *a): return "stock"
+        def voxel_pooling(self, g, x): return "stock"
+        def forward(self, x): return x
+
+    class Other(torch.nn.Module):
+        def forward(self, x): return x
+
+    m, o = ScriptModel(), Other()
+    keys = list(m.state_dict().keys())
+    assert patch.has_lss_surface(m) and not patch.has_lss_surface(o)
+    patch.install_everywhere()
+    try:
+        o(torch.zeros(1)); m(torch.zeros(1))
+    finally:
+        patch.uninstall_everywhere()
+    assert m.__dict__.get(patch._INSTALLED_ATTR) and not o.__dict__.get(patch._INSTALLED_ATTR)
+    assert m.voxel_pooling.__func__ is patch.voxel_pooling and m.get_geometry.__func__ is patch.get_geometry
+    assert list(m.state_dict().keys()) == keys               # nothing added to the checkpoint
+    # calibration-shaped call arguments are recognised (model(imgs, rots, trans, intrins, post_rots, post_trans))
+    B, N = 2, 6
+    args = (torch.zeros(B, N, 3, 8, 8), torch.zeros(B, N, 3, 3), torch.zeros(B, N, 3), torch.zeros(B, N, 3, 3),
+            torch.zeros(B, N, 3, 3), torch.zeros(B, N, 3))
+    assert not patch._looks_like_calibration(args)           # CPU tensors: nothing to prefetch
+    assert not patch._looks_like_calibration(args[:3])
+
+
+def test_make_frustum_and_hash_field_agree_with_their_twins():
+    import numpy as np
+    import torch
+    import lss_oracle as O
+    from lss2_multimodal_nu_b200 import functional as F, synthetic as S
+    for final_dim, dbound in (((128, 352), (4.0, 45.0, 1.0)), ((256, 704), (1.0, 60.0, 0.5))):
+        ours = F.make_frustum(final_dim, 16, dbound).numpy()
+        want = O.create_frustum(final_dim, 16, dbound)
+        assert ours.shape == want.shape and (ours.view(np.uint32) == want.view(np.uint32)).all()
+    idx = np.arange(0, 3_000_000_000, 7_654_321, dtype=np.int64)
+    a = S.hash_field_np(idx, 77)
+    b = S.hash_field_torch(torch.from_numpy(idx), 77).numpy()
+    assert (a.view(np.uint32) == b.view(np.uint32)).all() and a.min() >= -0.5 and a.max() < 0.5
