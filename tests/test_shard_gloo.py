@@ -36,6 +36,7 @@ def _worker(rank, world, port, out):
         # timing = max over ranks, throughput = all samples / slowest rank
         ms = 10.0 * (rank + 1)
         assert shard.max_over_ranks(ms) == 10.0 * world
+        assert shard.gather_floats(float(rank) + 0.5) == [r + 0.5 for r in range(world)]
         tput = shard.aggregate_throughput(8 * 100, ms)
         assert abs(tput - (8 * 100 * world) / (10.0 * world * 1e-3)) < 1e-6
         out[rank] = tput
