@@ -191,6 +191,9 @@ constexpr int kZeroBytes = 2048;  // zero block in shared memory: source of the 
 #ifndef LSS_FWD_M
 #define LSS_FWD_M 2
 #endif
+#ifndef LSS_BWD_PIPE_MAXV
+#define LSS_BWD_PIPE_MAXV 8
+#endif
 #ifndef LSS_BWD_MINB
 #define LSS_BWD_MINB 2
 #endif
@@ -628,9 +631,11 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
       dv = load_as_float(a.depth, dbase + (size_t)d * HW, a.depth_dtype);
     }
   };
-  int ncell;
-  float ndv;
-  load_bin(d_lo + sub, ncell, ndv);
+  // bins of the current round (A) and the next (B); the round after is loaded inside the loop
+  int cellA, cellB;
+  float dvA, dvB;
+  load_bin(d_lo + sub, cellA, dvA);
+  load_bin(d_lo + U + sub, cellB, dvB);
 #ifdef LSS_BWD_PREFETCH
   // the voxel lines of the whole slice are requested from DRAM now, all at once (L2 prefetch): the
   // rounds below then find them in L2 instead of paying one DRAM round trip per round
@@ -682,25 +687,40 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
   const float* gsrc2 = a.dbev + 4 * L * kNP + vsub * 2;
   const uint32_t Cw = static_cast<uint32_t>(a.C);
 
+  // kPipe (up to 8 channels per lane): rotating software pipeline -- bin u of the NEXT round is gathered
+  // as soon as bin u of this round has been consumed, so a gather has a round of arithmetic to arrive
+  // (long-scoreboard stalls 48 % -> 28 % of the samples at config 2).  Other row widths would spill: they
+  // gather at the top of their own round.
+  constexpr bool kPipe = kV > 4 && kV <= LSS_BWD_PIPE_MAXV;   // (4-channel lanes run at 64 registers: no room)
+  float4 gq[U][kNP > 0 ? kNP : 1];
+  float2 g2[U];
+  auto gather = [&](int u, int cells_of_round) {
+#ifdef LSS_DBG_BWD_CELL0
+    const int c = 0 * __shfl_sync(0xffffffffu, cells_of_round, g * L + u);
+#else
+    const int c = __shfl_sync(0xffffffffu, cells_of_round, g * L + u);
+#endif
+    const size_t off = (size_t)static_cast<uint32_t>(max(c, 0)) * Cw;              // dropped: any valid line, weight zero
+#pragma unroll
+    for (int p = 0; p < kNP; ++p) gq[u][p] = __ldg(reinterpret_cast<const float4*>(gsrc + off) + p * L);
+    if (kT2) g2[u] = __ldg(reinterpret_cast<const float2*>(gsrc2 + off));
+  };
+  if (kPipe) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) gather(u, cellA);
+  }
   for (int d0 = d_lo; d0 < d_hi; d0 += U) {
-    const int ccell = ncell;
-    const float cdv = (ccell >= 0) ? ndv : 0.f;             // dropped point: weight zero
-    load_bin(d0 + U + sub, ncell, ndv);                      // next round's bins, one round ahead
-    float4 gq[U][kNP > 0 ? kNP : 1];
-    float2 g2[U];
+    const int ccell = cellA;
+    const float cdv = (ccell >= 0) ? dvA : 0.f;             // dropped point: weight zero
+    int cellN;
+    float dvN;
+    load_bin(d0 + 2 * U + sub, cellN, dvN);                  // two rounds ahead
+    const bool more = kPipe && d0 + U < d_hi;                // warp-uniform
     float dv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-#ifdef LSS_DBG_BWD_CELL0
-      const int c = 0 * __shfl_sync(0xffffffffu, ccell, g * L + u);
-#else
-      const int c = __shfl_sync(0xffffffffu, ccell, g * L + u);
-#endif
       dv[u] = __shfl_sync(0xffffffffu, cdv, g * L + u);
-      const float* row = gsrc + (size_t)static_cast<uint32_t>(max(c, 0)) * Cw;   // dropped: any valid line, weight zero
-#pragma unroll
-      for (int p = 0; p < kNP; ++p) gq[u][p] = __ldg(reinterpret_cast<const float4*>(row) + p * L);
-      if (kT2) g2[u] = __ldg(reinterpret_cast<const float2*>(gsrc2 + (size_t)static_cast<uint32_t>(max(c, 0)) * Cw));
+      if (!kPipe) gather(u, ccell);
     }
     double dot[U];
 #pragma unroll
@@ -725,6 +745,7 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
         acc[4 * kNP + 1] = fmaf(dv[u], g2[u].y, acc[4 * kNP + 1]);
       }
       dot[u] = s;
+      if (more) gather(u, cellB);
     }
     // transposed butterfly over the walker's L lanes: halve the number of live dots per exchange
 #pragma unroll
@@ -754,6 +775,7 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
       else if (a.softmax) s_dd[crow][d] = r;                  // D <= kBwdMaxD (host)
       else store_from_float(a.ddepth, o, r, a.out_dtype);
     }
+    cellA = cellB; dvA = dvB; cellB = cellN; dvB = dvN;
   }
   // a non-finite gradient line shows in the float32 partial d_feat: poison this slice's d_depth
   {
