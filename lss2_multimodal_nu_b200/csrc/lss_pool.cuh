@@ -191,9 +191,6 @@ constexpr int kZeroBytes = 2048;  // zero block in shared memory: source of the 
 #ifndef LSS_FWD_M
 #define LSS_FWD_M 2
 #endif
-#ifndef LSS_BWD_PIPE_MAXV
-#define LSS_BWD_PIPE_MAXV 8
-#endif
 #ifndef LSS_BWD_MINB
 #define LSS_BWD_MINB 2
 #endif
@@ -687,40 +684,27 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
   const float* gsrc2 = a.dbev + 4 * L * kNP + vsub * 2;
   const uint32_t Cw = static_cast<uint32_t>(a.C);
 
-  // kPipe (up to 8 channels per lane): rotating software pipeline -- bin u of the NEXT round is gathered
-  // as soon as bin u of this round has been consumed, so a gather has a round of arithmetic to arrive
-  // (long-scoreboard stalls 48 % -> 28 % of the samples at config 2).  Other row widths would spill: they
-  // gather at the top of their own round.
-  constexpr bool kPipe = kV > 4 && kV <= LSS_BWD_PIPE_MAXV;   // (4-channel lanes run at 64 registers: no room)
-  float4 gq[U][kNP > 0 ? kNP : 1];
-  float2 g2[U];
-  auto gather = [&](int u, int cells_of_round) {
-#ifdef LSS_DBG_BWD_CELL0
-    const int c = 0 * __shfl_sync(0xffffffffu, cells_of_round, g * L + u);
-#else
-    const int c = __shfl_sync(0xffffffffu, cells_of_round, g * L + u);
-#endif
-    const size_t off = (size_t)static_cast<uint32_t>(max(c, 0)) * Cw;              // dropped: any valid line, weight zero
-#pragma unroll
-    for (int p = 0; p < kNP; ++p) gq[u][p] = __ldg(reinterpret_cast<const float4*>(gsrc + off) + p * L);
-    if (kT2) g2[u] = __ldg(reinterpret_cast<const float2*>(gsrc2 + off));
-  };
-  if (kPipe) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) gather(u, cellA);
-  }
   for (int d0 = d_lo; d0 < d_hi; d0 += U) {
     const int ccell = cellA;
     const float cdv = (ccell >= 0) ? dvA : 0.f;             // dropped point: weight zero
     int cellN;
     float dvN;
-    load_bin(d0 + 2 * U + sub, cellN, dvN);                  // two rounds ahead
-    const bool more = kPipe && d0 + U < d_hi;                // warp-uniform
+    load_bin(d0 + 2 * U + sub, cellN, dvN);                  // two rounds ahead: the gathers below never wait for a cell
+    float4 gq[U][kNP > 0 ? kNP : 1];
+    float2 g2[U];
     float dv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+#ifdef LSS_DBG_BWD_CELL0
+      const int c = 0 * __shfl_sync(0xffffffffu, ccell, g * L + u);
+#else
+      const int c = __shfl_sync(0xffffffffu, ccell, g * L + u);
+#endif
       dv[u] = __shfl_sync(0xffffffffu, cdv, g * L + u);
-      if (!kPipe) gather(u, ccell);
+      const size_t off = (size_t)static_cast<uint32_t>(max(c, 0)) * Cw;            // dropped: any valid line, weight zero
+#pragma unroll
+      for (int p = 0; p < kNP; ++p) gq[u][p] = __ldg(reinterpret_cast<const float4*>(gsrc + off) + p * L);
+      if (kT2) g2[u] = __ldg(reinterpret_cast<const float2*>(gsrc2 + off));
     }
     double dot[U];
 #pragma unroll
@@ -745,7 +729,6 @@ liftsplat_bwd_kernel(PoolBwdArgs a) {
         acc[4 * kNP + 1] = fmaf(dv[u], g2[u].y, acc[4 * kNP + 1]);
       }
       dot[u] = s;
-      if (more) gather(u, cellB);
     }
     // transposed butterfly over the walker's L lanes: halve the number of live dots per exchange
 #pragma unroll
