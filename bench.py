@@ -127,6 +127,7 @@ def run_reference_arm(args, cfg):
     # every step is one batch of the workload on all host cores (~50 ms): the requested steps / warm-up are
     # honoured up to a time budget that keeps the whole run within a few minutes
     r = cpu_port_run(cfg, max(1, args.steps), max(1, args.warmup), budget_s=150.0)
+    stock = reference_torch_cpu_leg(cfg)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["samples_per_s"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "steps_timed": r["steps"], "warmup": max(3, args.warmup),
@@ -138,8 +139,47 @@ def run_reference_arm(args, cfg):
                                    "reference algorithm (oracle/lss_oracle.c), OpenMP" % (cfg.B, r["steps"])},
         "e2e": {"value": r["samples_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # the slower of the two CPU baselines is reported beside the line's value, not as it
+        "reference_torch_cpu": stock,
     }
     print(json.dumps(line))
+
+
+def reference_torch_cpu_leg(cfg, steps=3):
+    """The UNMODIFIED reference class (oracle/_ref through oracle/ref_import.py) on the host cores: LSS.get_voxels
+    + backward with stock PyTorch CPU kernels, all threads.  Reported beside the C restatement, which is the
+    faster (hence the conservative) CPU baseline and stays the reference arm's `value`."""
+    try:
+        import torch
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_import
+        if not ref_import.available():
+            return {"unavailable": "reference tree not staged (oracle/stage_ref.py)"}
+        if cfg.C != 64:
+            return {"unavailable": "the reference's LSS class hard-codes camC = 64 (src/model_baseline.py:25)"}
+        from lss2_multimodal_nu_b200 import synthetic as S
+        torch.manual_seed(0)
+        m = ref_import.build_lss(cfg.B, cfg.grid_conf(), cfg.data_aug_conf()).train()
+        cal = [torch.from_numpy(v) for v in S.make_calibration(cfg, 1234).values()]
+        gen = torch.Generator(); gen.manual_seed(99)
+        x = torch.randn(cfg.B * cfg.N, 512, cfg.fH, cfg.fW, generator=gen).requires_grad_(True)
+        nx = [int(v) for v in m.nx]
+        dbev = torch.randn(cfg.B, cfg.C * nx[2], nx[0], nx[1], generator=gen)
+
+        def one():
+            x.grad = None
+            m.get_voxels(x, *cal).backward(dbev)
+        one()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        dt = (time.perf_counter() - t0) / steps
+        return {"value": cfg.B / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": steps,
+                "threads": torch.get_num_threads(), "kind": "reference",
+                "note": "UNMODIFIED reference LSS.get_voxels (src/model_baseline.py:128-133) forward + backward, "
+                        "stock PyTorch on the host cores"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:160]}
 
 
 # ---------------------------------------------------------------------------
