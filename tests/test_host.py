@@ -240,3 +240,29 @@ def test_make_frustum_and_hash_field_agree_with_their_twins():
     a = S.hash_field_np(idx, 77)
     b = S.hash_field_torch(torch.from_numpy(idx), 77).numpy()
     assert (a.view(np.uint32) == b.view(np.uint32)).all() and a.min() >= -0.5 and a.max() < 0.5
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the same metric, unit
+    and config as our arm, a CPU baseline description, zero copies, no GPU work -- it must run without a GPU."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    _sys.path.insert(0, root)
+    import bench
+    from lss2_multimodal_nu_b200 import synthetic as S
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
+    assert d["config"] == bench.base_config(S.config("config2"), 1, 4)          # what our arm prints for N = 1
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    stock = d["reference_torch_cpu"]
+    assert "unavailable" in stock or (stock["kind"] == "reference" and 0 < stock["value"] < d["value"] * 10)
