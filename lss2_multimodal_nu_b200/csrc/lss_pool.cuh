@@ -188,6 +188,9 @@ constexpr int kZeroBytes = 2048;  // zero block in shared memory: source of the 
 #ifndef LSS_FWD_MINB
 #define LSS_FWD_MINB 3
 #endif
+#ifndef LSS_FWD_U
+#define LSS_FWD_U 4
+#endif
 #ifndef LSS_FWD_M
 #define LSS_FWD_M 2
 #endif
@@ -308,13 +311,16 @@ __device__ __forceinline__ int first_bit_from(const uint32_t (&h)[kW], int pos) 
 }
 
 template <bool kFused, int L, int kNP, bool kT2, int kM>
-__global__ void __launch_bounds__(kPoolThreads, (kNP >= 3 ? 2 : LSS_FWD_MINB))
+__global__ void __launch_bounds__(kPoolThreads, (kNP >= 3 ? 2 : kT2 ? 4 : LSS_FWD_MINB))
 pool_fwd_kernel(PoolFwdArgs a) {
   constexpr int G = 32 / L;             // walkers per warp
   constexpr int kW = kM + 1;            // staged 32-record words: the chunk + one word of look-ahead
   constexpr int NR = kW * 32;
   constexpr int S = kM * 32 / G;        // records per walker (a divisor of 32 or 64)
-  constexpr int U = 4;                  // walk steps whose gathers are issued together
+  // walk steps whose gathers are issued together: 4 for rows of up to 64 floats; wider rows and the
+  // float4 + float2 layouts do better with 2 and the registers that frees (config 4: 260 -> 238 us,
+  // config 5: 1125 -> 1021 us; at C = 64 two steps cost the kernel alone 19.6 -> 21.2 us)
+  constexpr int U = (kT2 || kNP >= 3) ? 2 : LSS_FWD_U;
   static_assert(S >= 1 && (S <= 32 ? 32 % S == 0 : S == 64), "a walker's share is a whole number of mask words or a divisor of one");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
