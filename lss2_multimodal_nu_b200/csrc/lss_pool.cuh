@@ -194,6 +194,9 @@ constexpr int kZeroBytes = 2048;  // zero block in shared memory: source of the 
 #ifndef LSS_FWD_M
 #define LSS_FWD_M 2
 #endif
+#ifndef LSS_BWD_U2_MINV
+#define LSS_BWD_U2_MINV 16     // 16 channels per lane (C = 128): 2 bins per round fit the registers (config 5: 1143 -> 1081 us); 10 per lane: 4 is better (181 vs 238 us)
+#endif
 #ifndef LSS_BWD_MINB
 #define LSS_BWD_MINB 2
 #endif
@@ -597,9 +600,9 @@ __global__ void __launch_bounds__(32 * kBwdMaxWarps, (4 * kNP + (kT2 ? 2 : 0)) <
 liftsplat_bwd_kernel(PoolBwdArgs a) {
   constexpr int G = 32 / L;                     // pixels (walkers) per warp
   constexpr int kV = 4 * kNP + (kT2 ? 2 : 0);   // channels per lane
-  constexpr int U = (kV <= 4 && L >= 8) ? 8 : 4;   // depth bins per round (U <= L)
+  constexpr int U = (kV <= 4 && L >= 8) ? 8 : kV >= LSS_BWD_U2_MINV ? 2 : 4;   // depth bins per round (U <= L)
   constexpr int kLog = L == 32 ? 5 : L == 16 ? 4 : 3;
-  constexpr int kLogU = U == 8 ? 3 : 2;         // exchange levels that halve the live dots (kLogU <= kLog)
+  constexpr int kLogU = U == 8 ? 3 : U == 4 ? 2 : 1;   // exchange levels that halve the live dots (kLogU <= kLog)
   static_assert(L >= 8 && U <= L, "a walker's first U lanes hold the round's bins");
   __shared__ float s_df[kBwdMaxWarps][G * (L * kV)];         // the warp's partial d_feat
   __shared__ float s_dd[kGeneral ? G * kBwdMaxWarps : 1][kGeneral ? kBwdMaxD : 1];   // d_depth of the CTA's pixels (softmax)
